@@ -1,0 +1,322 @@
+"""GPU parity tests (``-m gpu``): the CUDA path, called through the C ABI (ctypes ->
+libvhr_b200.so), against the CPU oracle and the committed golden vectors.
+
+Tolerances (stated up front, SURVEY.md section 7 "hard parts"):
+  * integer / index / byte work (synthetic clips, masks, rectangle means of uint8 frames,
+    pyramid levels 1-2, chosen spectral bin, BPM value): bit-exact;
+  * float32 pixels (pyramid level >= 3, filtered/amplified level, magnified frames) and ROI
+    traces: max |a - b| <= 1e-4 * max |b| (relative to the tensor's scale).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import bpm as obpm
+from oracle import evm as oevm
+from oracle import roi as oroi
+from oracle import synth as osynth
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-4
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def eng(vhr):
+    e = vhr.Engine(0)
+    yield e
+    e.close()
+
+
+def spec_pair(vhr, **kw):
+    return vhr.SynthSpec(**kw), osynth.SynthParams(**kw)
+
+
+# ------------------------------------------------------------------------------------ synth
+@pytest.mark.parametrize("shape", [(7, 36, 64), (3, 61, 67), (5, 144, 256)])
+def test_synth_bit_identical(vhr, eng, shape):
+    T, H, W = shape
+    s, o = spec_pair(vhr, T=T, H=H, W=W, fps=5.0, pulse_hz=1.2, seed=3, clip=2, noise_sigma=2.0)
+    np.testing.assert_array_equal(s.pulse_table(), o.pulse_table())
+    got = eng.synth_clip(s).cpu().numpy()
+    np.testing.assert_array_equal(got, osynth.synth_frames(o))
+    part = eng.synth_clip(s, t0=2, t1=T).cpu().numpy()
+    np.testing.assert_array_equal(part, got[2:])
+
+
+# ---------------------------------------------------------------------------------- pyramid
+@pytest.mark.parametrize("hw", [(144, 256), (480, 640), (135, 248), (97, 131), (61, 67), (9, 16), (5, 7)])
+@pytest.mark.parametrize("levels", [1, 2, 3, 4])
+def test_pyrdown_cascade(vhr, eng, hw, levels):
+    import torch
+    H, W = hw
+    rng = np.random.default_rng(H * 31 + W + levels)
+    fr = rng.integers(0, 256, (3, H, W, 3), dtype=np.uint8)
+    got = eng.pyrdown(torch.as_tensor(fr, device=eng.tdev), levels).cpu().numpy()
+    ref = oevm.pyrdown_cascade(fr, levels)
+    assert got.shape == ref.shape                      # bit-exact level indexing / sizes
+    if levels <= 2:
+        np.testing.assert_array_equal(got, ref.astype(np.float32))    # exact integers * 2^-8l
+    else:
+        assert rel_err(got, ref) <= REL
+
+
+def test_pyrdown_many_frames_persistent_split(vhr, eng):
+    """More frames than CTAs can take whole: shares start and end mid-frame."""
+    import torch
+    rng = np.random.default_rng(11)
+    fr = rng.integers(0, 256, (700, 40, 64, 3), dtype=np.uint8)
+    got = eng.pyrdown(torch.as_tensor(fr, device=eng.tdev), 2).cpu().numpy()
+    np.testing.assert_array_equal(got, oevm.pyrdown_cascade(fr, 2).astype(np.float32))
+
+
+# --------------------------------------------------------------------------------- bandpass
+@pytest.mark.parametrize("case", [(150, 5.0, 432), (300, 30.0, 777), (299, 29.97, 64), (64, 10.0, 5), (1800, 30.0, 96)])
+def test_temporal_bandpass(vhr, eng, case):
+    import torch
+    T, fps, P = case
+    rng = np.random.default_rng(T)
+    t = np.arange(T) / fps
+    x = (150 + 20 * rng.standard_normal((1, P)) + rng.standard_normal((T, P))
+         + 1.5 * np.sin(2 * np.pi * 1.2 * t)[:, None]).astype(np.float32)
+    got = eng.bandpass(torch.as_tensor(x, device=eng.tdev), fps, 0.7, 4.0, gain=50.0).cpu().numpy()
+    ref = 50.0 * oevm.ideal_bandpass(x, fps, 0.7, 4.0)
+    assert rel_err(got, ref) <= REL
+    n, k0, k1 = eng.band_bins(T, fps, 0.7, 4.0)
+    bins = oevm.band_bins(T, fps, 0.7, 4.0)
+    assert (n, k0, k1) == (len(bins), int(bins[0]), int(bins[-1]))
+
+
+def test_bandpass_in_place_and_empty_band(vhr, eng):
+    import torch
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((100, 33)).astype(np.float32)
+    xd = torch.as_tensor(x, device=eng.tdev)
+    ref = oevm.ideal_bandpass(x, 10.0, 0.7, 4.0)
+    eng.bandpass(xd, 10.0, 0.7, 4.0, 1.0, out=xd)
+    assert rel_err(xd.cpu().numpy(), ref) <= REL
+    z = eng.bandpass(torch.as_tensor(x, device=eng.tdev), 10.0, 6.0, 7.0, 1.0).cpu().numpy()   # above Nyquist
+    assert np.all(z == 0)
+
+
+# --------------------------------------------------------------------------------- collapse
+@pytest.mark.parametrize("hw", [(144, 256), (135, 248), (97, 131), (480, 640), (33, 700)])
+@pytest.mark.parametrize("levels", [1, 3, 4])
+def test_collapse_addback(vhr, eng, hw, levels):
+    import torch
+    H, W = hw
+    rng = np.random.default_rng(H + W + levels)
+    T = 2
+    fr = rng.integers(0, 256, (T, H, W, 3), dtype=np.uint8)
+    wl, hl = oevm.pyr_dims(W, H, levels)[-1]
+    lv = (40 * rng.standard_normal((T, hl, wl, 3))).astype(np.float32)
+    rects = np.array([[[W // 4, H // 3, W // 4 + max(1, W // 3), H // 3 + max(1, H // 4)],
+                       [0, 0, W, H], [5, 2, 5, 9]]] * T, dtype=np.int32)
+    o32, o8, means = eng.collapse(torch.as_tensor(lv, device=eng.tdev), torch.as_tensor(fr, device=eng.tdev),
+                                  levels, out_f32=True, out_u8=True, rects=rects)
+    ref = oevm.collapse_addback(lv, fr, levels)
+    assert rel_err(o32.cpu().numpy(), ref) <= REL
+    # u8 output: the rounding rule is bit-exact wherever the float value is not within
+    # tolerance of a .5 boundary
+    ref8 = oevm.to_u8(ref)
+    got8 = o8.cpu().numpy()
+    frac = np.abs((np.clip(ref, 0, 255) + 0.5) % 1.0)
+    safe = (frac > 1e-3) & (frac < 1 - 1e-3)
+    np.testing.assert_array_equal(got8[safe], ref8[safe])
+    assert np.abs(got8.astype(int) - ref8.astype(int)).max() <= 1
+    m = means.cpu().numpy()
+    for t in range(T):
+        for k in range(2):
+            x1, y1, x2, y2 = rects[t, k]
+            exp = ref[t, y1:y2, x1:x2].reshape(-1, 3).mean(0)
+            assert np.abs(m[t, k] - exp).max() <= REL * np.abs(exp).max()
+        assert np.isnan(m[t, 2]).all()                 # empty rectangle -> NaN like np.mean([])
+
+
+def test_evm_end_to_end_c1(vhr, eng):
+    """Config c1 (256x144, 5 FPS, 30 s, 1.2 Hz): EVM + ROI + BPM against the oracle."""
+    s, o = spec_pair(vhr, T=150, H=144, W=256, fps=5.0, pulse_hz=1.2, seed=0)
+    fr = osynth.synth_frames(o)
+    frd = eng.synth_clip(s)
+    np.testing.assert_array_equal(frd.cpu().numpy(), fr)
+    lm = o.landmarks()
+    rect = oroi.cheek_roi_from_bbox(oroi.bbox_from_landmarks_clamped(lm[:, 0], lm[:, 1], 256, 144), 256, 144)
+    rects = np.tile(np.array(rect, dtype=np.int32), (150, 1, 1))
+    r = eng.evm(frd, 5.0, 4, 0.7, 4.0, 50.0, rects=rects, out_f32=True, keep_levels=True)
+    lv, filt, out = oevm.evm_clip(fr, 5.0, 4, 0.7, 4.0, 50.0)
+    assert rel_err(r["level"].cpu().numpy(), lv) <= REL
+    assert rel_err(r["filtered"].cpu().numpy(), filt) <= REL
+    assert rel_err(r["out_f32"].cpu().numpy(), out) <= REL
+    x1, y1, x2, y2 = rect
+    trace_ref = out[:, y1:y2, x1:x2, :].reshape(150, -1, 3).mean(1)
+    trace = r["roi_mean"].cpu().numpy()[:, 0]
+    assert rel_err(trace, trace_ref) <= REL
+    # BPM: identical bin, identical value
+    from video_heart_rate_b200.pipeline import ANALYSIS_BAND
+    bpm, kbin = eng.bpm_fft(r["roi_mean"][:, 0, 1].contiguous(), [0], [150], 5.0, ANALYSIS_BAND,
+                            detrend=vhr.DETREND_F32)
+    g32 = trace_ref[:, 1].astype(np.float32)
+    exp_bpm, exp_k, _ = obpm.estimate_bpm_analysis(g32 - np.mean(g32), 5.0)
+    assert int(kbin[0]) == exp_k and float(bpm[0]) == exp_bpm == 72.0
+
+
+# --------------------------------------------------------------------------------------- ROI
+def test_rect_means_golden(vhr, eng, golden_dir):
+    """Bit-exact against the reference's own process_frame / np.mean (golden vectors)."""
+    import torch
+    from video_heart_rate_b200 import host
+    from video_heart_rate_b200.pipeline import video_trace, green_avg_trace
+    g = np.load(os.path.join(golden_dir, "roi_rect.npz"))
+    for i in range(int(g["n_px"])):
+        frame = g[f"px_frame_{i}"]
+        lm = np.stack([g[f"px_xs_{i}"], g[f"px_ys_{i}"]], 1)
+        fr = torch.as_tensor(frame[None], device=eng.tdev)
+        means, _ = green_avg_trace(eng, fr, lm[None])
+        np.testing.assert_array_equal(means.cpu().numpy()[0], g[f"px_mean_clean_{i}"])
+        v = video_trace(eng, fr, lm[None], overdraw=True)
+        np.testing.assert_array_equal(v.cpu().numpy()[0], g[f"px_video_green_{i}"])
+
+
+def test_poly_mask_and_means(vhr, eng):
+    import torch
+    rng = np.random.default_rng(5)
+    H, W, T = 90, 120, 3
+    polys = np.zeros((T, 4, 12, 2), dtype=np.int32)
+    nv = np.zeros((T, 4), dtype=np.int32)
+    for t in range(T):
+        for k in range(4):
+            n = int(rng.integers(3, 12))
+            if k == 3:
+                n = int(rng.integers(0, 3))                      # degenerate: empty / point / segment
+            ang = np.sort(rng.uniform(0, 2 * np.pi, n))
+            r = rng.uniform(5, 60, n)
+            if k == 1:
+                r[::2] *= 0.4                                     # concave star
+            pts = np.stack([60 + r * np.cos(ang), 45 + r * np.sin(ang)], 1).astype(np.int32)   # partly off-frame
+            polys[t, k, :n] = pts
+            nv[t, k] = n
+    mask = eng.poly_mask(T, H, W, polys, nv).cpu().numpy()
+    fr8 = rng.integers(0, 256, (T, H, W, 3), dtype=np.uint8)
+    fr32 = (rng.standard_normal((T, H, W, 3)) * 50 + 120).astype(np.float32)
+    m8, c8 = eng.roi_mean_poly(torch.as_tensor(fr8, device=eng.tdev), polys, nv)
+    m32, c32 = eng.roi_mean_poly(torch.as_tensor(fr32, device=eng.tdev), polys, nv)
+    for t in range(T):
+        for k in range(4):
+            ref = oroi.poly_mask(H, W, polys[t, k, :nv[t, k]])
+            np.testing.assert_array_equal(mask[t, k].astype(bool), ref)          # bit-exact mask
+            assert int(c8[t, k]) == int(ref.sum()) == int(c32[t, k])
+            np.testing.assert_array_equal(m8[t, k].cpu().numpy(), oroi.masked_mean(fr8[t], ref))
+            e = oroi.masked_mean(fr32[t], ref)
+            if ref.sum():
+                assert np.abs(m32[t, k].cpu().numpy() - e).max() <= REL * np.abs(e).max()
+            else:
+                assert np.isnan(m32[t, k].cpu().numpy()).all()
+
+
+# --------------------------------------------------------------------------------------- BPM
+def test_bpm_golden(vhr, eng, golden_dir):
+    """Identical BPM (hence identical spectral-peak bin) as the reference's estimators on the
+    golden traces: analysis FFT, VIDEO FFT, Butterworth/Chebyshev/FIR + Welch, LIVE Welch."""
+    from video_heart_rate_b200.pipeline import ANALYSIS_BAND, LIVE_BAND, VIDEO_BAND, design_filters
+    g = np.load(os.path.join(golden_dir, "bpm.npz"))
+    bad = []
+    for i in range(int(g["n"])):
+        x, fps = g[f"x_{i}"], float(g[f"fps_{i}"])
+        exp = g[f"bpm_{i}"]
+        n = len(x)
+        a, _ = eng.bpm_fft(x, [0], [n], fps, ANALYSIS_BAND, detrend=vhr.DETREND_F32, mode=vhr.FFT_ANALYSIS)
+        v, _ = eng.bpm_fft(x, [0], [n], fps, VIDEO_BAND, detrend=vhr.DETREND_F64, mode=vhr.FFT_VIDEO)
+        f = design_filters(fps, VIDEO_BAND)
+        wb, _, fb = eng.bpm_welch(x, [0], [n], fps, VIDEO_BAND, vhr.DETREND_F64, vhr.FILT_SOS, f["butter"], want_filtered=True)
+        wc, _, fc = eng.bpm_welch(x, [0], [n], fps, VIDEO_BAND, vhr.DETREND_F64, vhr.FILT_SOS, f["cheby2"], want_filtered=True)
+        wf, _, ff = eng.bpm_welch(x, [0], [n], fps, VIDEO_BAND, vhr.DETREND_F64, vhr.FILT_FIR, f["fir"], want_filtered=True)
+        wl, _, _ = eng.bpm_welch(x, [0], [n], fps, LIVE_BAND, vhr.DETREND_F64, vhr.FILT_NONE)
+        got = np.array([float(q[0]) for q in (a, v, wb, wc, wf, wl)])
+        if not np.array_equal(got, exp, equal_nan=True):
+            bad.append((i, fps, n, got, exp))
+        # filtered traces: float64 recurrences, same operation order as scipy
+        assert rel_err(fb.cpu().numpy()[0], g[f"fb_{i}"]) <= 1e-9
+        assert rel_err(fc.cpu().numpy()[0], g[f"fc_{i}"]) <= 1e-9
+        if g[f"ff_{i}"].size:
+            assert rel_err(ff.cpu().numpy()[0], g[f"ff_{i}"]) <= 1e-9
+        else:
+            assert np.isnan(float(wf[0]))
+    assert not bad, f"{len(bad)} traces differ, first: {bad[:3]}"
+
+
+def test_live_sos_golden(vhr, eng, golden_dir):
+    import torch
+    g = np.load(os.path.join(golden_dir, "bpm.npz"))
+    for j in range(2):
+        sos = g[f"live_sos_{j}"]
+        x = g[f"live_x_{j}"]
+        state = torch.zeros((sos.shape[0], 2), dtype=torch.float64, device=eng.tdev)
+        y1 = eng.sos_causal(x[:150], sos, state).cpu().numpy()
+        y2 = eng.sos_causal(x[150:], sos, state).cpu().numpy()          # carried state
+        assert rel_err(np.concatenate([y1, y2]), g[f"live_y_{j}"]) <= 1e-12
+
+
+def test_green_avg_measure_matches_oracle(vhr, eng):
+    """analysis green_avg.measure() body on a synthetic clip: identical (M,2) array."""
+    from video_heart_rate_b200.pipeline import green_avg_measure
+    for fps, T in ((5.0, 150), (30.0, 420)):
+        s, o = spec_pair(vhr, T=T, H=72, W=128, fps=fps, pulse_hz=1.3, seed=4)
+        fr = osynth.synth_frames(o)
+        lm = o.landmarks()
+        got = green_avg_measure(eng, fr, fps, lm)
+        rect = oroi.cheek_roi_from_bbox(oroi.bbox_from_landmarks_clamped(lm[:, 0], lm[:, 1], 128, 72), 128, 72)
+        green = [oroi.rect_mean(f, rect)[1] for f in fr]
+        exp, _ = obpm.green_avg_series(green, fps)
+        np.testing.assert_array_equal(got, exp)
+
+
+def test_video_bpm_series_matches_oracle(vhr, eng):
+    """rppg_VIDEO.py sliding-window block over a trace: identical BPM triplets."""
+    from video_heart_rate_b200.pipeline import video_bpm_series
+    rng = np.random.default_rng(8)
+    for fps, n in ((30.0, 420), (5.0, 90)):
+        t = np.arange(n) / fps
+        g = 120 + np.sin(2 * np.pi * 1.25 * t) + 0.2 * rng.standard_normal(n)
+        got = video_bpm_series(eng, g, fps)
+        exp = obpm.video_window_bpm(g, fps)
+        assert len(exp) == len(got["frame"])
+        for j, (i, b1, b2, b3, _) in enumerate(exp):
+            assert got["frame"][j] == i
+            assert got["butter"][j] == b1 and got["cheby2"][j] == b2
+            assert (np.isnan(got["fir"][j]) and b3 is None) or got["fir"][j] == b3
+
+
+def test_dropin_functions(vhr, eng):
+    """Reference-named functions (rppg.py) behave like the reference's on one window."""
+    from video_heart_rate_b200 import rppg
+    rng = np.random.default_rng(3)
+    fps = 30.0
+    t = np.arange(300) / fps
+    x = np.sin(2 * np.pi * 1.2 * t) + 0.1 * rng.standard_normal(300)
+    for ours, ref in ((rppg.bandpass_butterworth(x, fps, 0.7, 2, 2), obpm.bandpass_butterworth(x, fps, 0.7, 2, 2)),
+                      (rppg.bandpass_cheby2(x, fps, 0.7, 2), obpm.bandpass_cheby2(x, fps, 0.7, 2)),
+                      (rppg.bandpass_fir(x, fps, 0.7, 2), obpm.bandpass_fir(x, fps, 0.7, 2))):
+        assert rel_err(ours, ref) <= 1e-9
+    assert rppg.estimate_bpm_welch(x, fps) == obpm.estimate_bpm_welch(x, fps)[0]
+    assert rppg.estimate_bpm(x, fps) == obpm.estimate_bpm_video_fft(x, fps)[0]
+    with pytest.raises(ValueError):
+        rppg.bandpass_fir(x[:50], 5.0, 0.7, 2)              # reference raises at 5 FPS (padlen 123)
+    roi = rng.integers(0, 256, (25, 89, 3), dtype=np.uint8)
+    assert rppg.get_avg(roi, 1) == float(np.mean(roi[:, :, 1]))
+
+
+def test_evm_roi_host_matches_device_path(vhr, eng):
+    s, o = spec_pair(vhr, T=60, H=72, W=128, fps=10.0, pulse_hz=1.5, seed=9)
+    fr = osynth.synth_frames(o)
+    rects = np.tile(np.array([[40, 30, 90, 50]], dtype=np.int32), (60, 1, 1))
+    means = eng.evm_roi_host(fr, 10.0, rects, levels=3)
+    import torch
+    r = eng.evm(torch.as_tensor(fr, device=eng.tdev), 10.0, 3, 0.7, 4.0, 50.0, rects=rects)
+    np.testing.assert_array_equal(means, r["roi_mean"].cpu().numpy())       # same kernels, deterministic

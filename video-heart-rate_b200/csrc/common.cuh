@@ -1,0 +1,82 @@
+// Shared declarations for libvhr_b200.so (sm_100a).  See include/vhr_b200.h for the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+#include "../../include/vhr_b200.h"
+
+struct vhr_ctx {
+    int device = 0;
+    int num_sms = 148;
+    int smem_optin = 0;
+    char err[512] = {0};
+    std::atomic<int64_t> launches{0};
+    // scratch arena (device), grown on demand outside the hot loop
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    // cached twiddle table for the temporal bandpass
+    float2* tw = nullptr;
+    int tw_T = 0;
+    // context-owned buffers of the *_host convenience path
+    void* hostpath = nullptr;
+    size_t hostpath_bytes = 0;
+};
+
+void vhr_set_error(vhr_ctx* ctx, const char* fmt, ...);
+int vhr_scratch(vhr_ctx* ctx, size_t bytes, void** out);
+
+#define VHR_CHECK_CUDA(ctx, expr)                                                        \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            vhr_set_error(ctx, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,              \
+                          cudaGetErrorString(_e));                                       \
+            return VHR_ERR_CUDA;                                                         \
+        }                                                                                \
+    } while (0)
+
+#define VHR_REQUIRE(ctx, cond, msg)                                                      \
+    do {                                                                                 \
+        if (!(cond)) {                                                                   \
+            vhr_set_error(ctx, "%s: %s", __func__, msg);                                 \
+            return VHR_ERR_INVALID;                                                      \
+        }                                                                                \
+    } while (0)
+
+#define VHR_LAUNCHED(ctx, n) (ctx)->launches.fetch_add((n), std::memory_order_relaxed)
+
+static inline int vhr_after_launch(vhr_ctx* ctx, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        vhr_set_error(ctx, "launch %s -> %s", what, cudaGetErrorString(e));
+        return VHR_ERR_CUDA;
+    }
+    VHR_LAUNCHED(ctx, 1);
+    return VHR_OK;
+}
+
+__host__ __device__ static inline int vhr_reflect101(int i, int n) {
+    // BORDER_REFLECT_101 for |excursion| < n (all uses here: excursion <= 2)
+    if (n == 1) return 0;
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+    if (i < 0) i = -i;            // n == 2, i == 3 -> -1 -> 1
+    return i;
+}
+
+struct PyrDims {
+    int w[VHR_MAX_LEVELS + 1];
+    int h[VHR_MAX_LEVELS + 1];
+};
+static inline PyrDims vhr_make_dims(int W, int H, int levels) {
+    PyrDims d;
+    d.w[0] = W;
+    d.h[0] = H;
+    for (int l = 1; l <= VHR_MAX_LEVELS; ++l) {
+        d.w[l] = l <= levels ? (d.w[l - 1] + 1) / 2 : 0;
+        d.h[l] = l <= levels ? (d.h[l - 1] + 1) / 2 : 0;
+    }
+    return d;
+}

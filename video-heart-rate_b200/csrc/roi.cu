@@ -1,0 +1,231 @@
+// ROI reductions on raw frames: rectangle means (reference-pinned) and polygon means / masks
+// (frozen exact-integer rule; the reference has no polygon ROI).
+//
+// Rectangles replace np.mean(roi[:, :, c]) of rppg_VIDEO.py:60-66 / green_avg.py:34: the sum
+// of uint8 values is an exact integer, and float64(sum) / float64(count) is one IEEE
+// division -- bit-identical to NumPy's float64 pairwise mean.  The optional paint list
+// reproduces the reference's overdraw quirk (rppg_VIDEO.py:54,100-106: the bbox, forehead
+// and cheek outlines are drawn INTO the frame before the cheek slice is averaged) using the
+// thickness-2 cv.rectangle raster model pinned in oracle/roi.py:outline_mask.
+#include "common.cuh"
+
+namespace {
+
+constexpr int RT = 256;
+constexpr int MAXPAINT = 8;
+
+struct PaintArgs {
+    int np;
+    uint8_t rgb[MAXPAINT][3];
+};
+
+__device__ __forceinline__ bool on_outline(int x, int y, int x1, int y1, int x2, int y2) {
+    const int xa = min(x1, x2), xb = max(x1, x2), ya = min(y1, y2), yb = max(y1, y2);
+    const bool horiz = (abs(y - ya) <= 1 || abs(y - yb) <= 1) && x >= xa && x <= xb;
+    const bool vert = (abs(x - xa) <= 1 || abs(x - xb) <= 1) && y >= ya && y <= yb;
+    return horiz || vert;
+}
+
+template <typename Tsum>
+__device__ __forceinline__ Tsum block_sum(Tsum v, Tsum* sh) {
+    // fixed-order tree: warp shuffle then warp 0 over the warp totals
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[wid] = v;
+    __syncthreads();
+    Tsum r = 0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) r += sh[w];
+    return r;   // valid in thread 0
+}
+
+__global__ void __launch_bounds__(RT) rect_mean_u8_kernel(const uint8_t* __restrict__ frames, int H, int W,
+                                                           const int32_t* __restrict__ rects, int K,
+                                                           const int32_t* __restrict__ paint, PaintArgs pa,
+                                                           double* __restrict__ mean) {
+    __shared__ unsigned long long sh[RT / 32];
+    const int t = blockIdx.x / K, k = blockIdx.x - t * K;
+    const int32_t* rc = rects + ((size_t)t * K + k) * 4;
+    const int x1 = rc[0], y1 = rc[1], x2 = rc[2], y2 = rc[3];
+    const int rw = x2 - x1, rh = y2 - y1;
+    double* out = mean + ((size_t)t * K + k) * 3;
+    if (rw <= 0 || rh <= 0 || x1 < 0 || y1 < 0 || x2 > W || y2 > H) {
+        if (threadIdx.x < 3) out[threadIdx.x] = __longlong_as_double(0x7FF8000000000000ll);
+        return;
+    }
+    int prc[MAXPAINT][4];
+    for (int p = 0; p < pa.np; ++p)
+        for (int q = 0; q < 4; ++q) prc[p][q] = paint[((size_t)t * pa.np + p) * 4 + q];
+    const uint8_t* fr = frames + (size_t)t * H * W * 3;
+    unsigned long long s0 = 0, s1 = 0, s2 = 0;
+    const int npx = rw * rh;
+    for (int idx = threadIdx.x; idx < npx; idx += RT) {
+        const int r = idx / rw, c = idx - r * rw;
+        const int x = x1 + c, y = y1 + r;
+        const uint8_t* p = fr + ((size_t)y * W + x) * 3;
+        unsigned v0 = p[0], v1 = p[1], v2 = p[2];
+        for (int q = 0; q < pa.np; ++q) {
+            if (on_outline(x, y, prc[q][0], prc[q][1], prc[q][2], prc[q][3])) {
+                v0 = pa.rgb[q][0]; v1 = pa.rgb[q][1]; v2 = pa.rgb[q][2];
+            }
+        }
+        s0 += v0; s1 += v1; s2 += v2;
+    }
+    const unsigned long long t0 = block_sum(s0, sh);
+    const unsigned long long t1 = block_sum(s1, sh);
+    const unsigned long long t2 = block_sum(s2, sh);
+    if (threadIdx.x == 0) {
+        const double n = (double)npx;
+        out[0] = __ddiv_rn((double)t0, n);
+        out[1] = __ddiv_rn((double)t1, n);
+        out[2] = __ddiv_rn((double)t2, n);
+    }
+}
+
+// ---- polygons ----------------------------------------------------------------------------
+// inside(x,y) = on any edge (closed segment) OR even-odd parity with half-open spans
+// (y0 <= y) != (y1 <= y) and the pixel strictly left of the crossing -- oracle/roi.py:poly_mask.
+__device__ __forceinline__ bool poly_inside(int x, int y, const int2* __restrict__ v, int n) {
+    bool on = false, par = false;
+    for (int i = 0; i < n; ++i) {
+        const int2 a = v[i], b = v[i + 1 == n ? 0 : i + 1];
+        const long long dx = (long long)b.x - a.x, dy = (long long)b.y - a.y;
+        const long long cr = dx * ((long long)y - a.y) - dy * ((long long)x - a.x);
+        on |= (cr == 0) && x >= min(a.x, b.x) && x <= max(a.x, b.x) && y >= min(a.y, b.y) && y <= max(a.y, b.y);
+        if (dy != 0) {
+            const bool strad = (a.y <= y) != (b.y <= y);
+            // tt = (x - x0) dy - dx (y - y0) = -cr
+            const bool left = (dy > 0) ? (cr > 0) : (cr < 0);
+            par ^= (strad && left);
+        }
+    }
+    return on || par;
+}
+
+template <typename Tpix>
+__global__ void __launch_bounds__(RT) poly_mean_kernel(const Tpix* __restrict__ frames, int H, int W,
+                                                        const int32_t* __restrict__ poly, const int32_t* __restrict__ nvert,
+                                                        int K, int Vmax, double* __restrict__ mean, long long* __restrict__ count) {
+    __shared__ int2 verts[VHR_MAX_POLY_VERTS];
+    __shared__ double shd[RT / 32];
+    __shared__ unsigned long long shu[RT / 32];
+    const int t = blockIdx.x / K, k = blockIdx.x - t * K;
+    int n = nvert[(size_t)t * K + k];
+    n = min(max(n, 0), min(Vmax, VHR_MAX_POLY_VERTS));
+    const int32_t* pv = poly + (((size_t)t * K + k) * Vmax) * 2;
+    for (int i = threadIdx.x; i < n; i += RT) verts[i] = make_int2(pv[2 * i], pv[2 * i + 1]);
+    __syncthreads();
+    int bx0 = W, by0 = H, bx1 = -1, by1 = -1;
+    for (int i = 0; i < n; ++i) {
+        bx0 = min(bx0, verts[i].x); bx1 = max(bx1, verts[i].x);
+        by0 = min(by0, verts[i].y); by1 = max(by1, verts[i].y);
+    }
+    bx0 = max(bx0, 0); by0 = max(by0, 0); bx1 = min(bx1, W - 1); by1 = min(by1, H - 1);
+    const int bw = bx1 - bx0 + 1, bh = by1 - by0 + 1;
+    const Tpix* fr = frames + (size_t)t * H * W * 3;
+    double s0 = 0, s1 = 0, s2 = 0;
+    unsigned long long u0 = 0, u1 = 0, u2 = 0, cnt = 0;
+    if (n > 0 && bw > 0 && bh > 0) {
+        const int npx = bw * bh;
+        for (int idx = threadIdx.x; idx < npx; idx += RT) {
+            const int r = idx / bw, c = idx - r * bw;
+            const int x = bx0 + c, y = by0 + r;
+            if (poly_inside(x, y, verts, n)) {
+                const Tpix* p = fr + ((size_t)y * W + x) * 3;
+                if (sizeof(Tpix) == 1) { u0 += (unsigned)p[0]; u1 += (unsigned)p[1]; u2 += (unsigned)p[2]; }
+                else { s0 += (double)p[0]; s1 += (double)p[1]; s2 += (double)p[2]; }
+                ++cnt;
+            }
+        }
+    }
+    const unsigned long long ctot = block_sum(cnt, shu);
+    double t0, t1, t2;
+    if (sizeof(Tpix) == 1) {
+        t0 = (double)block_sum(u0, shu); t1 = (double)block_sum(u1, shu); t2 = (double)block_sum(u2, shu);
+    } else {
+        t0 = block_sum(s0, shd); t1 = block_sum(s1, shd); t2 = block_sum(s2, shd);
+    }
+    if (threadIdx.x == 0) {
+        double* out = mean + ((size_t)t * K + k) * 3;
+        if (ctot == 0) {
+            out[0] = out[1] = out[2] = __longlong_as_double(0x7FF8000000000000ll);
+        } else {
+            const double nn = (double)ctot;
+            out[0] = __ddiv_rn(t0, nn); out[1] = __ddiv_rn(t1, nn); out[2] = __ddiv_rn(t2, nn);
+        }
+        if (count) count[(size_t)t * K + k] = (long long)ctot;
+    }
+}
+
+__global__ void __launch_bounds__(RT) poly_mask_kernel(int H, int W, const int32_t* __restrict__ poly,
+                                                        const int32_t* __restrict__ nvert, int K, int Vmax,
+                                                        uint8_t* __restrict__ mask) {
+    __shared__ int2 verts[VHR_MAX_POLY_VERTS];
+    const int tk = blockIdx.y;
+    int n = nvert[tk];
+    n = min(max(n, 0), min(Vmax, VHR_MAX_POLY_VERTS));
+    const int32_t* pv = poly + ((size_t)tk * Vmax) * 2;
+    for (int i = threadIdx.x; i < n; i += RT) verts[i] = make_int2(pv[2 * i], pv[2 * i + 1]);
+    __syncthreads();
+    const int npx = H * W;
+    for (int idx = blockIdx.x * RT + threadIdx.x; idx < npx; idx += gridDim.x * RT) {
+        const int y = idx / W, x = idx - y * W;
+        mask[(size_t)tk * npx + idx] = (n > 0 && poly_inside(x, y, verts, n)) ? 1 : 0;
+    }
+}
+
+}  // namespace
+
+extern "C" int vhr_roi_mean_rect_u8(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int W,
+                                    const int32_t* d_rects, int K, const int32_t* d_paint, int NP,
+                                    const uint8_t* paint_rgb, double* d_mean, void* stream) {
+    VHR_REQUIRE(ctx, ctx != nullptr, "null context");
+    VHR_REQUIRE(ctx, d_frames && d_rects && d_mean, "null pointer");
+    VHR_REQUIRE(ctx, T >= 1 && H >= 1 && W >= 1 && K >= 1, "bad shape");
+    VHR_REQUIRE(ctx, NP >= 0 && NP <= MAXPAINT, "too many paint rectangles (max 8)");
+    VHR_REQUIRE(ctx, NP == 0 || (d_paint && paint_rgb), "paint pointers missing");
+    PaintArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.np = NP;
+    for (int p = 0; p < NP; ++p)
+        for (int c = 0; c < 3; ++c) pa.rgb[p][c] = paint_rgb[p * 3 + c];
+    rect_mean_u8_kernel<<<(unsigned)((size_t)T * K), RT, 0, (cudaStream_t)stream>>>(d_frames, H, W, d_rects, K, d_paint, pa, d_mean);
+    return vhr_after_launch(ctx, "rect_mean_u8_kernel");
+}
+
+template <typename Tpix>
+static int poly_mean_impl(vhr_ctx* ctx, const Tpix* d_frames, int T, int H, int W, const int32_t* d_poly,
+                          const int32_t* d_nvert, int K, int Vmax, double* d_mean, int64_t* d_count, void* stream) {
+    VHR_REQUIRE(ctx, ctx != nullptr, "null context");
+    VHR_REQUIRE(ctx, d_frames && d_poly && d_nvert && d_mean, "null pointer");
+    VHR_REQUIRE(ctx, T >= 1 && H >= 1 && W >= 1 && K >= 1, "bad shape");
+    VHR_REQUIRE(ctx, Vmax >= 1 && Vmax <= VHR_MAX_POLY_VERTS, "Vmax must be 1..64");
+    poly_mean_kernel<Tpix><<<(unsigned)((size_t)T * K), RT, 0, (cudaStream_t)stream>>>(
+        d_frames, H, W, d_poly, d_nvert, K, Vmax, d_mean, reinterpret_cast<long long*>(d_count));
+    return vhr_after_launch(ctx, "poly_mean_kernel");
+}
+
+extern "C" int vhr_roi_mean_poly_u8(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int W, const int32_t* d_poly,
+                                    const int32_t* d_nvert, int K, int Vmax, double* d_mean, int64_t* d_count, void* stream) {
+    return poly_mean_impl<uint8_t>(ctx, d_frames, T, H, W, d_poly, d_nvert, K, Vmax, d_mean, d_count, stream);
+}
+
+extern "C" int vhr_roi_mean_poly_f32(vhr_ctx* ctx, const float* d_frames, int T, int H, int W, const int32_t* d_poly,
+                                     const int32_t* d_nvert, int K, int Vmax, double* d_mean, int64_t* d_count, void* stream) {
+    return poly_mean_impl<float>(ctx, d_frames, T, H, W, d_poly, d_nvert, K, Vmax, d_mean, d_count, stream);
+}
+
+extern "C" int vhr_poly_mask(vhr_ctx* ctx, int T, int H, int W, const int32_t* d_poly, const int32_t* d_nvert, int K,
+                             int Vmax, uint8_t* d_mask, void* stream) {
+    VHR_REQUIRE(ctx, ctx != nullptr, "null context");
+    VHR_REQUIRE(ctx, d_poly && d_nvert && d_mask, "null pointer");
+    VHR_REQUIRE(ctx, T >= 1 && H >= 1 && W >= 1 && K >= 1, "bad shape");
+    VHR_REQUIRE(ctx, Vmax >= 1 && Vmax <= VHR_MAX_POLY_VERTS, "Vmax must be 1..64");
+    VHR_REQUIRE(ctx, (long long)T * K <= 65535, "T*K too large for one mask call");
+    const int npx = H * W;
+    dim3 grid((unsigned)min((npx + RT - 1) / RT, 1024), (unsigned)(T * K));
+    poly_mask_kernel<<<grid, RT, 0, (cudaStream_t)stream>>>(H, W, d_poly, d_nvert, K, Vmax, d_mask);
+    return vhr_after_launch(ctx, "poly_mask_kernel");
+}

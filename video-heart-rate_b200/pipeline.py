@@ -1,0 +1,138 @@
+"""Clip-level pipelines: the reference's per-frame loops restated as batched device work.
+
+``green_avg_measure``   analysis/measurement/green_avg.py:11-52 (the measure() plugin body)
+``video_bpm_series``    rppg_VIDEO.py:354-416 signal part (process_frame + sliding window)
+``evm_bpm``             EVM (pyramid -> ideal bandpass -> collapse) + ROI mean + BPM, the
+                        BASELINE.json configs c2/c4 (no reference code for the EVM part)
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import host
+from .engine import (DETREND_F32, DETREND_F64, DETREND_NONE, FFT_ANALYSIS, FILT_FIR, FILT_NONE, FILT_SOS, Engine)
+
+VIDEO_BAND = (0.7, 2.0)                 # rppg_VIDEO.py:33-34
+LIVE_BAND = (40 / 60, 150 / 60)         # rppg_LIVESTREAM.py:34-35
+ANALYSIS_BAND = (40 / 60, 200 / 60)     # analysis/utils/estimate_bpm.py:6-7
+EVM_BAND = (0.7, 4.0)                   # BASELINE.json configs
+# paint colours of rppg_VIDEO.py:100 (bbox, green) and :54 (forehead, cheek: blue) in BGR
+VIDEO_PAINT_BGR = ((0, 255, 0), (255, 0, 0), (255, 0, 0))
+
+
+def _frames_to_device(eng: Engine, frames):
+    import torch
+    if isinstance(frames, torch.Tensor):
+        return frames.to(eng.tdev).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(frames), device=eng.tdev)
+
+
+def green_avg_trace(eng: Engine, frames, landmarks, valid=None):
+    """Per-frame cheek-ROI channel means (T,3) float64 (device) the analysis way: clamped
+    bbox -> cheek rectangle -> mean (analysis/utils/roi.py:43-59,104-109; green_avg.py:34).
+    Returns (means, usable)."""
+    fr = _frames_to_device(eng, frames)
+    T, H, W, _ = fr.shape
+    lm = np.asarray(landmarks, dtype=np.float64)
+    if lm.ndim == 2:
+        lm = np.broadcast_to(lm, (T,) + lm.shape)
+    usable = np.ones(T, dtype=bool)
+    if valid is not None:
+        lm, usable = host.hold_landmarks(lm, valid)
+    rects = host.slice_rects(host.cheek_roi_clamped(host.bbox_clamped(lm, W, H), W, H), W, H)
+    means = eng.roi_mean_rect(fr, rects[:, None, :])[:, 0, :]
+    return means, usable
+
+
+def green_avg_measure(eng: Engine, frames, fps: float, landmarks, valid=None, channel: int = 1,
+                      window_s: float = 30.0, acq_s: float = 10.0, band=ANALYSIS_BAND) -> np.ndarray:
+    """analysis/measurement/green_avg.py:measure on decoded frames + landmarks -> (M,2)
+    float64 [t_sec, bpm]."""
+    import torch
+    means, usable = green_avg_trace(eng, frames, landmarks, valid)
+    green = means[:, channel]
+    idx_all = np.arange(green.shape[0])
+    if not usable.all():
+        keep = torch.as_tensor(np.nonzero(usable)[0], device=eng.tdev)
+        green = green[keep].contiguous()
+        idx_all = idx_all[usable]
+    n = int(green.shape[0])
+    fi, st, ln = host.green_avg_windows(n, fps, window_s, acq_s)
+    if len(fi) == 0:
+        return np.zeros((0, 2))
+    bpm, _ = eng.bpm_fft(green, st, ln, fps, band, detrend=DETREND_F32, mode=FFT_ANALYSIS)
+    bpm = bpm.cpu().numpy()
+    ok = ~np.isnan(bpm)                                   # `if bpm is not None` (green_avg.py:47)
+    ts = idx_all[fi] * (1 / fps)                          # ts = i * (1 / fps)  (green_avg.py:48)
+    return np.column_stack([ts[ok], bpm[ok]])
+
+
+def video_trace(eng: Engine, frames_bgr, landmarks, overdraw: bool = True, channel: int = 1):
+    """The value process_frame appends per frame (rppg_VIDEO.py:91-110): mean of ``channel``
+    over the unclamped cheek slice, by default with the outline-overdraw quirk.  (T,) device."""
+    fr = _frames_to_device(eng, frames_bgr)
+    T, H, W, _ = fr.shape
+    lm = np.asarray(landmarks, dtype=np.float64)
+    if lm.ndim == 2:
+        lm = np.broadcast_to(lm, (T,) + lm.shape)
+    bb = host.bbox_video(lm, W, H)
+    fh = host.roi_coords(bb, *host.FOREHEAD)
+    ck = host.roi_coords(bb, *host.CHEEK)
+    rects = host.slice_rects(ck, W, H)[:, None, :]
+    if overdraw:
+        paint = np.stack([bb, fh, ck], 1).astype(np.int32)
+        means = eng.roi_mean_rect(fr, rects, paint=paint, paint_rgb=np.asarray(VIDEO_PAINT_BGR, dtype=np.uint8))
+    else:
+        means = eng.roi_mean_rect(fr, rects)
+    return means[:, 0, channel].contiguous()
+
+
+def design_filters(fps: float, band=VIDEO_BAND):
+    """Coefficient design exactly where the reference designs them (rppg_VIDEO.py:252,266,284):
+    Butterworth order 2 and Chebyshev-II order 4 / 40 dB as SOS, 41-tap Hamming FIR."""
+    import scipy.signal as sp
+    nyq = 0.5 * fps
+    lo, hi = band[0] / nyq, band[1] / nyq
+    return {"butter": sp.butter(2, [lo, hi], btype="band", output="sos"),
+            "cheby2": sp.cheby2(4, 40, [lo, hi], btype="band", output="sos"),
+            "fir": sp.firwin(41, [lo, hi], pass_zero=False, window="hamming")}
+
+
+def video_bpm_series(eng: Engine, green, fps: float, band=VIDEO_BAND, window_seconds: float = 10):
+    """rppg_VIDEO.py:392-409 over a whole trace: every frame once the deque holds more than
+    ``window_len`` samples -> dict(frame (M,), butter (M,), cheby2 (M,), fir (M,)) BPM arrays
+    (NaN where the reference raises / returns None) and the chosen bins."""
+    import torch
+    g = green if isinstance(green, torch.Tensor) else torch.as_tensor(np.asarray(green, dtype=np.float64), device=eng.tdev)
+    fi, st, ln = host.video_windows(int(g.numel()), fps, window_seconds)
+    out = {"frame": fi}
+    if len(fi) == 0:
+        for k in ("butter", "cheby2", "fir"):
+            out[k] = np.zeros(0)
+            out[k + "_bin"] = np.zeros(0, dtype=np.int32)
+        return out
+    f = design_filters(fps, band)
+    for name, kind in (("butter", FILT_SOS), ("cheby2", FILT_SOS), ("fir", FILT_FIR)):
+        bpm, kbin, _ = eng.bpm_welch(g, st, ln, fps, band, detrend=DETREND_F64, filt_kind=kind, coef=f[name])
+        out[name] = bpm.cpu().numpy()
+        out[name + "_bin"] = kbin.cpu().numpy()
+    return out
+
+
+def evm_bpm(eng: Engine, frames, fps: float, rects, levels: int = 4, band=EVM_BAND, alpha: float = 50.0,
+            channel: int = 1, window_len: int | None = None, hop: int | None = None, bpm_band=ANALYSIS_BAND,
+            out_f32=True, out_u8=False):
+    """EVM + ROI + BPM on device-resident frames.  ``rects`` (T,K,4) already sliced to the
+    frame.  The BPM comes from the green mean of ROI 0 of the MAGNIFIED frames through the
+    analysis estimator (float32 detrend + FFT peak, green_avg.py:42-44 / estimate_bpm.py) over
+    sliding windows (default: one window = the whole clip).
+    -> dict(roi_mean (T,K,3) device, bpm (n_win,), bin (n_win,), out_f32/out_u8)."""
+    fr = _frames_to_device(eng, frames)
+    T = fr.shape[0]
+    r = eng.evm(fr, fps, levels, band[0], band[1], alpha, rects=rects, out_f32=out_f32, out_u8=out_u8)
+    green = r["roi_mean"][:, 0, channel].contiguous()
+    wl = T if window_len is None else window_len
+    st, ln = host.sliding_windows(T, wl, wl if hop is None else hop)
+    bpm, kbin = eng.bpm_fft(green, st, ln, fps, bpm_band, detrend=DETREND_F32, mode=FFT_ANALYSIS)
+    r.update({"bpm": bpm, "bin": kbin, "win_start": st, "win_len": ln})
+    return r
