@@ -36,9 +36,9 @@ struct BpArgs {
 __global__ void __launch_bounds__(NTHREADS) bandpass_dft_kernel(const BpArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* xs = reinterpret_cast<float*>(smem_raw);                    // [T][PX]
-    float2* tw = reinterpret_cast<float2*>(xs + (size_t)a.T * PX);     // [T]
-    float* Xr = reinterpret_cast<float*>(tw + a.T);                    // [nb][PX]
+    float* Xr = xs + (size_t)a.T * PX;                                 // [nb][PX]  (16-byte aligned: float4 loads)
     float* Xi = Xr + (size_t)a.nb * PX;                                // [nb][PX]
+    float2* tw = reinterpret_cast<float2*>(Xi + (size_t)a.nb * PX);    // [T]
     const int T = a.T;
     const long long p0 = (long long)blockIdx.x * PX;
     const int npx = (int)min((long long)PX, a.P - p0);

@@ -23,50 +23,62 @@ constexpr int MAXCOEF = (MAXSEC * 6 > MAXTAPS) ? MAXSEC * 6 : MAXTAPS;
 
 __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7FF8000000000000ll); }
 
-// numpy's pairwise summation for float32 (numpy/_core/src/umath/loops_utils.h.src), which is
-// what np.mean / np.nanmean of a contiguous float32 vector evaluates.
-__device__ float pairwise_sum_f32(const float* a, int n) {
+// numpy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src), which is what np.mean /
+// np.nanmean of a contiguous float vector evaluates.  The recursion (split at n/2 rounded
+// down to a multiple of 8 until blocks are <= 128 long) is run with an explicit stack: device
+// recursion would need more than the default per-thread stack.
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+
+template <typename F>
+__device__ F pairwise_leaf(const F* a, int n) {
     if (n < 8) {
-        float res = 0.f;
-        for (int i = 0; i < n; ++i) res = __fadd_rn(res, a[i]);
+        F res = (F)0;
+        for (int i = 0; i < n; ++i) res = add_rn(res, a[i]);
         return res;
-    } else if (n <= 128) {
-        float r[8];
-        for (int j = 0; j < 8; ++j) r[j] = a[j];
-        int i;
-        for (i = 8; i < n - (n % 8); i += 8)
-            for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], a[i + j]);
-        float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
-                              __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
-        for (; i < n; ++i) res = __fadd_rn(res, a[i]);
-        return res;
-    } else {
-        int n2 = n / 2;
-        n2 -= n2 % 8;
-        return __fadd_rn(pairwise_sum_f32(a, n2), pairwise_sum_f32(a + n2, n - n2));
     }
-}
-__device__ double pairwise_sum_f64(const double* a, int n) {
-    if (n < 8) {
-        double res = 0.;
-        for (int i = 0; i < n; ++i) res = __dadd_rn(res, a[i]);
-        return res;
-    } else if (n <= 128) {
-        double r[8];
-        for (int j = 0; j < 8; ++j) r[j] = a[j];
-        int i;
-        for (i = 8; i < n - (n % 8); i += 8)
-            for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], a[i + j]);
-        double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                               __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-        for (; i < n; ++i) res = __dadd_rn(res, a[i]);
-        return res;
-    } else {
-        int n2 = n / 2;
-        n2 -= n2 % 8;
-        return __dadd_rn(pairwise_sum_f64(a, n2), pairwise_sum_f64(a + n2, n - n2));
+    F r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = add_rn(r[j], a[i + j]);
     }
+    F res = add_rn(add_rn(add_rn(r[0], r[1]), add_rn(r[2], r[3])), add_rn(add_rn(r[4], r[5]), add_rn(r[6], r[7])));
+    for (; i < n; ++i) res = add_rn(res, a[i]);
+    return res;
 }
+
+template <typename F>
+__device__ F pairwise_sum(const F* a, int n) {
+    if (n <= 128) return pairwise_leaf(a, n);
+    int s_off[40], s_len[40];
+    bool s_comb[40];
+    F vals[40];
+    int sp = 0, vp = 0;
+    s_off[sp] = 0; s_len[sp] = n; s_comb[sp] = false; ++sp;
+    while (sp > 0) {
+        --sp;
+        const int off = s_off[sp], len = s_len[sp];
+        if (s_comb[sp]) {
+            const F r = vals[--vp];
+            const F l = vals[--vp];
+            vals[vp++] = add_rn(l, r);
+        } else if (len <= 128) {
+            vals[vp++] = pairwise_leaf(a + off, len);
+        } else {
+            int n2 = len / 2;
+            n2 -= n2 % 8;
+            s_off[sp] = off; s_len[sp] = len; s_comb[sp] = true; ++sp;              // combine after both halves
+            s_off[sp] = off + n2; s_len[sp] = len - n2; s_comb[sp] = false; ++sp;    // right half (evaluated second)
+            s_off[sp] = off; s_len[sp] = n2; s_comb[sp] = false; ++sp;               // left half (evaluated first)
+        }
+    }
+    return vals[0];
+}
+__device__ __forceinline__ float pairwise_sum_f32(const float* a, int n) { return pairwise_sum<float>(a, n); }
+__device__ __forceinline__ double pairwise_sum_f64(const double* a, int n) { return pairwise_sum<double>(a, n); }
 
 // frequency of bin k exactly as numpy.fft.fftfreq / rfftfreq compute it:
 //   val = 1.0 / (n * d), d = 1 / fs ; f = k * val
@@ -142,9 +154,9 @@ struct FftArgs {
 __global__ void __launch_bounds__(BT) bpm_fft_kernel(const FftArgs a) {
     extern __shared__ __align__(16) unsigned char sm[];
     __shared__ ArgMax shm[BT / 32];
-    double* x = reinterpret_cast<double*>(sm);                       // [max_len]
-    double2* tw = reinterpret_cast<double2*>(x + a.max_len);         // [max_len]
-    float* xf = reinterpret_cast<float*>(tw + a.max_len);            // [max_len]
+    double2* tw = reinterpret_cast<double2*>(sm);                    // [max_len]  (16-byte aligned first)
+    double* x = reinterpret_cast<double*>(tw + a.max_len);           // [max_len]
+    float* xf = reinterpret_cast<float*>(x + a.max_len);             // [max_len]
     const int w = blockIdx.x;
     const int s = a.start[w], n = a.len[w];
     const bool bad = (n < 1) || n > a.max_len || s < 0 || s + n > a.n_trace || (a.mode == VHR_FFT_ANALYSIS && n < 8);
@@ -244,11 +256,11 @@ __global__ void __launch_bounds__(BT) bpm_welch_kernel(const __grid_constant__ W
     const double* c_coef = a.coef;
     extern __shared__ __align__(16) unsigned char sm[];
     __shared__ ArgMax shm[BT / 32];
-    double* x = reinterpret_cast<double*>(sm);                        // [max_len]   window / filtered
+    double2* tw = reinterpret_cast<double2*>(sm);                     // [max_len]   (16-byte aligned first)
+    double* x = reinterpret_cast<double*>(tw + a.max_len);            // [max_len]   window / filtered
     double* ext = x + a.max_len;                                      // [max_ext]   padded signal
     double* ext2 = ext + a.max_ext;                                   // [max_ext]   FIR scratch
-    double2* tw = reinterpret_cast<double2*>(ext2 + a.max_ext);       // [max_len]
-    double* win = reinterpret_cast<double*>(tw + a.max_len);          // [max_len]   hann
+    double* win = ext2 + a.max_ext;                                   // [max_len]   hann
     float* xf = reinterpret_cast<float*>(win + a.max_len);            // [max_len]
     const int w = blockIdx.x;
     const int s = a.start[w], n = a.len[w];

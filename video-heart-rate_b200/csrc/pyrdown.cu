@@ -158,8 +158,8 @@ struct Stream {
             f = max(0, 2 * f - 2);
             next[l] = f;
         }
-        l1_ready_for = -1;
-        pre_for = -1;
+        l1_ready_for = -100;      // sentinels must not collide with r - 1 for r = 0
+        pre_for = -100;
     }
 
     // ---- level 1 -------------------------------------------------------------------------
@@ -196,7 +196,7 @@ struct Stream {
                 load_row<ALIGNED>(a, frame, vhr_reflect101(2 * r + 4, a.H), i, pre[1]);
                 pre_for = r + 1;
             } else {
-                pre_for = -1;
+                pre_for = -100;
             }
             // vertical pass, packed 16-bit lanes (max 65280: no carry between halves)
             uint32_t v[6];
