@@ -7,27 +7,35 @@
 // walking back the pyrDown chain.  The fused ROI mean replaces get_avg over the cheek slice
 // (rppg_VIDEO.py:60-66,106-110) evaluated on the magnified frame.
 //
-// Design (DESIGN.md "collapse"): this kernel moves 15 of the 18 bytes per pixel of the
-// whole EVM path (3 B/px read, 12 B/px written), so it is laid out around the output store:
-//   * CTA = one 320 x 32 pixel tile of one frame; thread = 4 consecutive floats of a row
-//     (one 16-byte store, one 4-byte load of the original pixels), marching down the rows.
-//   * The pyrUp halo is one sample per level, so the whole chain for a tile (level L region
-//     of ~23x5 samples up to a level-1 region of ~163x19) is rebuilt in shared memory per
-//     tile; levels 1..L-1 never touch HBM.
-//   * The last expansion is evaluated on the fly: horizontally (3 taps from the level-1
-//     tile in smem, once per level-1 row) and vertically (3-row register window), fused
-//     with the uint8 -> float conversion, the add-back and the store.
+// Design (DESIGN.md "collapse"): this kernel moves 15 of the 18 bytes per pixel of the whole
+// EVM path (3 B/px read, 12 B/px written) and was instruction-bound in its first form, so it
+// is organised to minimise instructions per output value:
+//   * CTA = one TW x 32 pixel tile of one frame.  The pyrUp halo is one sample per level, so
+//     the whole chain for a tile (level-L region of a few samples up to a level-1 region of
+//     (TW/2+6) x 20) is rebuilt in shared memory; levels 1..L-1 never touch HBM.  Levels are
+//     stored PLANAR (channel planes) and each expansion step maps one thread to one source
+//     cell producing its 2x2 destination block (27 loads -> 12 values).
+//   * Last expansion: one work item = 4 pixels x 2 rows (24 values): 18 LDS.64 from the
+//     level-1 planes, vertical then horizontal interpolation in registers, uint8 -> float by
+//     byte-permute + one add, add-back fused into the last FMA, three 16-byte stores per row.
+//     No sliding window: items are independent, registers stay low, occupancy high.
+//   * Frame-border fix-ups (reflect/replicate) and the ROI accumulation are compiled as
+//     separate loop bodies selected by block-uniform flags, so interior tiles pay for neither.
 //   * ROI sums: per-thread float accumulators -> warp shuffle -> per-tile partial (double)
 //     -> fixed-order finalize kernel.  No atomics: results are run-to-run identical.
 #include "common.cuh"
 
 namespace {
 
-constexpr int TW = 320;                 // tile width in pixels (960 floats = 4 per thread)
-constexpr int TH = 32;                  // tile height (even)
-constexpr int NT = TW * 3 / 4;          // 240 threads own columns
-constexpr int NTL = 256;                // launched threads (whole warps for the shuffles)
+constexpr int TH = 32;                  // tile height (rows); even
+constexpr int MAXT = 320;               // max threads per CTA
 constexpr int KMAXF = 4;                // fused ROI rectangles per call
+
+struct LevelGeom {            // storage geometry of one level's region in shared memory
+    int ro, co;               // image row / col stored at index 0
+    int rs, ps;               // row stride, plane stride (floats)
+    int off;                  // float offset of plane 0 in dynamic smem
+};
 
 struct ColArgs {
     const float* lvl;
@@ -37,6 +45,7 @@ struct ColArgs {
     int T, H, W, L;
     int w[VHR_MAX_LEVELS + 1];
     int h[VHR_MAX_LEVELS + 1];
+    int TW;                   // tile width in pixels (multiple of 128)
     int tiles_x, tiles_y;
     const int32_t* rects;     // (T,K,4)
     int K;
@@ -45,245 +54,279 @@ struct ColArgs {
     int vec_ok;               // W % 4 == 0 and bases aligned
 };
 
-// one axis of pyrUp: destination index d -> up to 3 (source index, weight) taps
-struct Tap3 {
-    int i0, i1, i2;
-    float w0, w1, w2;
-};
-__device__ __forceinline__ Tap3 up_taps(int d, int n) {
-    Tap3 t;
-    const int m = d >> 1;
-    const int mp = (m + 1 >= n) ? n - 1 : m + 1;                 // replicate high side
-    if ((d & 1) == 0) {
-        const int mm = (m - 1 < 0) ? (n > 1 ? 1 : 0) : m - 1;    // reflect-101 low side
-        t.i0 = mm; t.i1 = m; t.i2 = mp;
-        t.w0 = 0.125f; t.w1 = 0.75f; t.w2 = 0.125f;
-    } else {
-        t.i0 = m; t.i1 = mp; t.i2 = mp;
-        t.w0 = 0.5f; t.w1 = 0.5f; t.w2 = 0.0f;
+// border-mapped neighbours of source index p on an axis of length n (cv2.pyrUp rule)
+__device__ __forceinline__ int nb_lo(int p, int n) { return (p - 1 < 0) ? (n > 1 ? 1 : 0) : p - 1; }
+__device__ __forceinline__ int nb_hi(int p, int n) { return (p + 1 >= n) ? n - 1 : p + 1; }
+
+// one expansion step in shared memory: every source cell (p,i) of level l+1 produces the 2x2
+// destination block (2p..2p+1, 2i..2i+1) of level l, all three channel planes.
+__device__ __forceinline__ void expand_level(const float* __restrict__ smf, const LevelGeom& s, int sn_h, int sn_w,
+                                             float* __restrict__ smw, const LevelGeom& d, int p_lo, int p_hi,
+                                             int i_lo, int i_hi, int tid, int nthreads) {
+    const int ni = i_hi - i_lo + 1;
+    const int ncell = (p_hi - p_lo + 1) * ni;
+    for (int cell = tid; cell < ncell; cell += nthreads) {
+        const int pr = cell / ni;
+        const int p = p_lo + pr, i = i_lo + (cell - pr * ni);
+        const int r0 = (nb_lo(p, sn_h) - s.ro) * s.rs, r1 = (min(p, sn_h - 1) - s.ro) * s.rs, r2 = (nb_hi(p, sn_h) - s.ro) * s.rs;
+        const int c0 = nb_lo(i, sn_w) - s.co, c1 = min(i, sn_w - 1) - s.co, c2 = nb_hi(i, sn_w) - s.co;
+        const int dbase = (2 * p - d.ro) * d.rs + (2 * i - d.co);
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const float* sp = smf + s.off + ch * s.ps;
+            float he[3], ho[3];
+            const int rr[3] = {r0, r1, r2};
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const float x0 = sp[rr[q] + c0], x1 = sp[rr[q] + c1], x2 = sp[rr[q] + c2];
+                he[q] = fmaf(x0 + x2, 0.125f, x1 * 0.75f);
+                ho[q] = (x1 + x2) * 0.5f;
+            }
+            float* dp = smw + d.off + ch * d.ps + dbase;
+            dp[0] = fmaf(he[0] + he[2], 0.125f, he[1] * 0.75f);
+            dp[1] = fmaf(ho[0] + ho[2], 0.125f, ho[1] * 0.75f);
+            dp[d.rs] = (he[1] + he[2]) * 0.5f;
+            dp[d.rs + 1] = (ho[1] + ho[2]) * 0.5f;
+        }
     }
-    return t;
 }
 
 template <int KMAX, bool F32OUT, bool U8OUT>
-__global__ void __launch_bounds__(NTL) collapse_kernel(const ColArgs a) {
-    extern __shared__ __align__(16) float smf[];
-    __shared__ float red[NTL / 32][KMAXF][3];
+struct Tile {
+    const ColArgs& a;
+    int t, x0, x1, y0, y1;
+    // level-1 geometry
+    const float* l1;
+    int l1_rs, l1_ps, l1_ro;
+    int n1w, n1h;
+    // ROI (block-uniform)
+    int rx1[KMAXF > 0 ? KMAXF : 1], ry1[KMAXF > 0 ? KMAXF : 1], rx2[KMAXF > 0 ? KMAXF : 1], ry2[KMAXF > 0 ? KMAXF : 1];
+    bool hit[KMAXF > 0 ? KMAXF : 1];
+    float acc[KMAXF > 0 ? KMAXF : 1][3];
 
+    __device__ Tile(const ColArgs& a_) : a(a_) {}
+
+    // one work item: pixels X..X+3, rows 2m and 2m+1
+    template <bool EDGE, bool ROI, bool VEC>
+    __device__ __forceinline__ void item(int X, int m, int colofs) {
+        const int rm = (nb_lo(m, n1h) - l1_ro) * l1_rs, rc = (m - l1_ro) * l1_rs, rp = (nb_hi(m, n1h) - l1_ro) * l1_rs;
+        float ve[3][4], vo[3][4];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const float* pl = l1 + ch * l1_ps + colofs;
+            const float2 a0 = *reinterpret_cast<const float2*>(pl + rm), a1 = *reinterpret_cast<const float2*>(pl + rm + 2);
+            const float2 b0 = *reinterpret_cast<const float2*>(pl + rc), b1 = *reinterpret_cast<const float2*>(pl + rc + 2);
+            const float2 c0 = *reinterpret_cast<const float2*>(pl + rp), c1 = *reinterpret_cast<const float2*>(pl + rp + 2);
+            const float av[4] = {a0.x, a0.y, a1.x, a1.y}, bv[4] = {b0.x, b0.y, b1.x, b1.y}, cv[4] = {c0.x, c0.y, c1.x, c1.y};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                ve[ch][j] = fmaf(av[j] + cv[j], 0.125f, bv[j] * 0.75f);
+                vo[ch][j] = (bv[j] + cv[j]) * 0.5f;
+            }
+            if (EDGE) {
+                const int J = X >> 1;
+                if (J + 1 >= n1w) { ve[ch][2] = ve[ch][1]; vo[ch][2] = vo[ch][1]; }           // replicate high side
+                if (J + 2 >= n1w) { ve[ch][3] = ve[ch][2]; vo[ch][3] = vo[ch][2]; }
+                if (J - 1 < 0) { ve[ch][0] = ve[ch][2]; vo[ch][0] = vo[ch][2]; }              // reflect-101: col -1 -> col 1
+            }
+        }
+        const size_t row_elems = (size_t)a.W * 3;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int y = 2 * m + half;
+            if (y < y0 || y >= y1) continue;          // tile rows start even; only the frame's last odd row can be cut
+            const size_t g = ((size_t)t * a.H + y) * row_elems + (size_t)X * 3;
+            uint32_t w0, w1, w2;
+            if (VEC) {
+                const uint32_t* fp = reinterpret_cast<const uint32_t*>(a.frames + g);
+                w0 = __ldg(fp); w1 = __ldg(fp + 1); w2 = __ldg(fp + 2);
+            } else {
+                w0 = w1 = w2 = 0;
+#pragma unroll
+                for (int k = 0; k < 12; ++k) {
+                    if (X + k / 3 < x1) {
+                        const uint32_t bv = __ldg(a.frames + g + k);
+                        if (k < 4) w0 |= bv << (8 * k); else if (k < 8) w1 |= bv << (8 * (k - 4)); else w2 |= bv << (8 * (k - 8));
+                    }
+                }
+            }
+            const uint32_t ww[3] = {w0, w1, w2};
+            float o[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                const int px = k / 3, ch = k - 3 * px;
+                // uint8 -> float: 0x4B0000xx = 2^23 + xx
+                const float f = __uint_as_float(__byte_perm(ww[k >> 2], 0x4B000000u, 0x7440 + (k & 3))) - 8388608.0f;
+                const float (&v)[4] = half ? vo[ch] : ve[ch];
+                float up;
+                if (px == 0) up = fmaf(v[0] + v[2], 0.125f, fmaf(v[1], 0.75f, f));
+                else if (px == 1) up = fmaf(v[1] + v[2], 0.5f, f);
+                else if (px == 2) up = fmaf(v[1] + v[3], 0.125f, fmaf(v[2], 0.75f, f));
+                else up = fmaf(v[2] + v[3], 0.5f, f);
+                o[k] = up;
+            }
+            if (F32OUT) {
+                if (VEC) {
+                    float4* op = reinterpret_cast<float4*>(a.out_f32 + g);
+                    op[0] = make_float4(o[0], o[1], o[2], o[3]);
+                    op[1] = make_float4(o[4], o[5], o[6], o[7]);
+                    op[2] = make_float4(o[8], o[9], o[10], o[11]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 12; ++k)
+                        if (X + k / 3 < x1) a.out_f32[g + k] = o[k];
+                }
+            }
+            if (U8OUT) {
+                uint32_t q[3] = {0, 0, 0};
+#pragma unroll
+                for (int k = 0; k < 12; ++k) {
+                    const float v = fminf(fmaxf(o[k], 0.0f), 255.0f);
+                    q[k >> 2] |= (uint32_t)(int)(v + 0.5f) << (8 * (k & 3));
+                }
+                if (VEC) {
+                    uint32_t* op = reinterpret_cast<uint32_t*>(a.out_u8 + g);
+                    op[0] = q[0]; op[1] = q[1]; op[2] = q[2];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 12; ++k)
+                        if (X + k / 3 < x1) a.out_u8[g + k] = (uint8_t)(q[k >> 2] >> (8 * (k & 3)));
+                }
+            }
+            if (ROI && KMAX > 0) {
+#pragma unroll
+                for (int k = 0; k < KMAX; ++k) {
+                    if (hit[k] && y >= ry1[k] && y < ry2[k]) {
+#pragma unroll
+                        for (int px = 0; px < 4; ++px) {
+                            if (X + px >= rx1[k] && X + px < rx2[k] && X + px < x1) {
+                                acc[k][0] += o[3 * px]; acc[k][1] += o[3 * px + 1]; acc[k][2] += o[3 * px + 2];
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    template <bool EDGE, bool ROI, bool VEC>
+    __device__ __forceinline__ void run(int colofs_base) {
+        const int cx = threadIdx.x, X = x0 + 4 * cx;
+        if (X >= x1) return;
+        const int colofs = colofs_base + 2 * cx;
+        for (int m = (y0 >> 1) + threadIdx.y; 2 * m < y1; m += blockDim.y) item<EDGE, ROI, VEC>(X, m, colofs);
+    }
+};
+
+template <int KMAX, bool F32OUT, bool U8OUT>
+__global__ void __launch_bounds__(MAXT, 3) collapse_kernel(const ColArgs a) {
+    extern __shared__ __align__(16) float smf[];
+    __shared__ float red[MAXT / 32][KMAXF][3];
+
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int nthreads = blockDim.x * blockDim.y;
     const int tiles = a.tiles_x * a.tiles_y;
     const int t = blockIdx.x / tiles;
     const int tile = blockIdx.x - t * tiles;
     const int by = tile / a.tiles_x, bx = tile - by * a.tiles_x;
-    const int x0 = bx * TW, x1 = min(a.W, x0 + TW);
+    const int x0 = bx * a.TW, x1 = min(a.W, x0 + a.TW);
     const int y0 = by * TH, y1 = min(a.H, y0 + TH);
     const int L = a.L;
 
-    // regions [ra,rb] x [ca,cb] needed at each level (inclusive)
+    // regions [ra,rb] x [ca,cb] needed at each level (inclusive) and their smem storage
     int ra[VHR_MAX_LEVELS + 1], rb[VHR_MAX_LEVELS + 1], ca[VHR_MAX_LEVELS + 1], cb[VHR_MAX_LEVELS + 1];
-    ra[0] = y0; rb[0] = y1 - 1; ca[0] = x0; cb[0] = x1 - 1;
+    LevelGeom g[VHR_MAX_LEVELS + 1];
+    ra[0] = y0; rb[0] = y1 - 1; ca[0] = x0; cb[0] = x0 + a.TW - 1;   // full tile width: partial tiles still index within it
     for (int l = 1; l <= L; ++l) {
         ra[l] = max(0, (ra[l - 1] >> 1) - 1);
         rb[l] = min(a.h[l] - 1, (rb[l - 1] >> 1) + 1);
         ca[l] = max(0, (ca[l - 1] >> 1) - 1);
         cb[l] = min(a.w[l] - 1, (cb[l - 1] >> 1) + 1);
+        if (cb[l] < ca[l]) cb[l] = ca[l];            // partial tile far right of a tiny level
+        LevelGeom& q = g[l];
+        q.ro = ra[l] & ~1;                            // 2x2 blocks start on even rows / cols
+        q.co = (ca[l] & ~1) - 1;                      // odd origin: the pairs (J-1,J) read by the last stage are 8-byte aligned
+        const int nrows = (rb[l] | 1) - q.ro + 1;
+        q.rs = (((cb[l] | 1) + 3 - q.co + 1) + 1) & ~1;       // +3: slack columns read (and discarded) at the frame edge
+        q.ps = nrows * q.rs;
+        q.off = (l & 1) ? a.buf_odd_off : a.buf_even_off;
     }
 
-    // ---- level L region from HBM -------------------------------------------------------
+    // ---- level L region from HBM (interleaved) into planar smem ---------------------------
     {
-        float* dst = smf + ((L & 1) ? a.buf_odd_off : a.buf_even_off);
+        const LevelGeom& q = g[L];
         const int rw = (cb[L] - ca[L] + 1) * 3, rh = rb[L] - ra[L] + 1;
         const float* src = a.lvl + ((size_t)t * a.h[L] * a.w[L]) * 3;
-        for (int idx = threadIdx.x; idx < rw * rh; idx += NTL) {
-            int r = idx / rw, j = idx - r * rw;
-            dst[idx] = __ldg(src + ((size_t)(ra[L] + r) * a.w[L] + ca[L]) * 3 + j);
+        for (int idx = tid; idx < rw * rh; idx += nthreads) {
+            const int r = idx / rw, j = idx - r * rw;
+            const int c = j / 3, ch = j - 3 * c;
+            smf[q.off + ch * q.ps + (ra[L] + r - q.ro) * q.rs + (ca[L] + c - q.co)] =
+                __ldg(src + ((size_t)(ra[L] + r) * a.w[L] + ca[L]) * 3 + j);
         }
     }
-    // ---- levels L-1 .. 1 in shared memory ----------------------------------------------
+    // ---- levels L-1 .. 1 in shared memory ----------------------------------------------------
     for (int l = L - 1; l >= 1; --l) {
         __syncthreads();
-        const float* src = smf + (((l + 1) & 1) ? a.buf_odd_off : a.buf_even_off);
-        float* dst = smf + ((l & 1) ? a.buf_odd_off : a.buf_even_off);
-        const int sw = (cb[l + 1] - ca[l + 1] + 1) * 3;
-        const int dwp = cb[l] - ca[l] + 1, dh = rb[l] - ra[l] + 1;
-        const int nsrc_h = a.h[l + 1], nsrc_w = a.w[l + 1];
-        for (int idx = threadIdx.x; idx < dwp * dh; idx += NTL) {
-            const int r = idx / dwp, xq = idx - r * dwp;
-            const Tap3 tv = up_taps(ra[l] + r, nsrc_h);
-            const Tap3 th = up_taps(ca[l] + xq, nsrc_w);
-            const float* r0 = src + (tv.i0 - ra[l + 1]) * sw;
-            const float* r1 = src + (tv.i1 - ra[l + 1]) * sw;
-            const float* r2 = src + (tv.i2 - ra[l + 1]) * sw;
-            const int c0 = (th.i0 - ca[l + 1]) * 3, c1 = (th.i1 - ca[l + 1]) * 3, c2 = (th.i2 - ca[l + 1]) * 3;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                float v0 = tv.w0 * r0[c0 + c] + tv.w1 * r1[c0 + c] + tv.w2 * r2[c0 + c];
-                float v1 = tv.w0 * r0[c1 + c] + tv.w1 * r1[c1 + c] + tv.w2 * r2[c1 + c];
-                float v2 = tv.w0 * r0[c2 + c] + tv.w1 * r1[c2 + c] + tv.w2 * r2[c2 + c];
-                dst[idx * 3 + c] = th.w0 * v0 + th.w1 * v1 + th.w2 * v2;
-            }
-        }
+        expand_level(smf, g[l + 1], a.h[l + 1], a.w[l + 1], smf, g[l], g[l].ro >> 1, rb[l] >> 1, (g[l].co + 1) >> 1,
+                     cb[l] >> 1, tid, nthreads);
     }
     __syncthreads();
 
-    // ---- last expansion fused with add-back, store and ROI sums ---------------------------
-    // L >= 1: source = level-1 region (buf_odd); n1w/n1h = level-1 size
-    const float* l1 = smf + a.buf_odd_off;
-    const int l1w = (cb[1] - ca[1] + 1) * 3;
-    const int n1w = a.w[1], n1h = a.h[1];
-    const int fbase = 4 * threadIdx.x;                 // first flat float of this thread in the tile row
-    int off[4][3];
-    float wg[4][3];
-    int gx[4], ch[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int f = fbase + j;
-        const int px = f / 3;
-        ch[j] = f - px * 3;
-        gx[j] = x0 + px;
-        const int gxc = min(gx[j], x1 - 1);          // threads past the tile edge stay in range
-        const Tap3 th = up_taps(gxc, n1w);
-        off[j][0] = (th.i0 - ca[1]) * 3 + ch[j];
-        off[j][1] = (th.i1 - ca[1]) * 3 + ch[j];
-        off[j][2] = (th.i2 - ca[1]) * 3 + ch[j];
-        wg[j][0] = th.w0; wg[j][1] = th.w1; wg[j][2] = th.w2;
-    }
-    const bool any_valid = gx[0] < x1;
-    const bool all_valid = gx[3] < x1;
-
-    auto hrow = [&](int r, float (&v)[4]) {
-        const float* rp = l1 + (r - ra[1]) * l1w;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = wg[j][0] * rp[off[j][0]] + wg[j][1] * rp[off[j][1]] + wg[j][2] * rp[off[j][2]];
-    };
-
-    // ROI bookkeeping (block-uniform)
-    int rx1[KMAXF], ry1[KMAXF], rx2[KMAXF], ry2[KMAXF];
-    bool hit[KMAXF];
-    float acc[KMAXF][4];
+    // ---- last expansion fused with add-back, store and ROI sums -------------------------------
+    Tile<KMAX, F32OUT, U8OUT> tl(a);
+    tl.t = t; tl.x0 = x0; tl.x1 = x1; tl.y0 = y0; tl.y1 = y1;
+    tl.l1 = smf + g[1].off; tl.l1_rs = g[1].rs; tl.l1_ps = g[1].ps; tl.l1_ro = g[1].ro;
+    tl.n1w = a.w[1]; tl.n1h = a.h[1];
+    bool any_hit = false;
     if (KMAX > 0) {
 #pragma unroll
         for (int k = 0; k < KMAX; ++k) {
-            hit[k] = false;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[k][j] = 0.f;
+            tl.hit[k] = false;
+            tl.acc[k][0] = tl.acc[k][1] = tl.acc[k][2] = 0.f;
             if (k < a.K) {
                 const int32_t* rc = a.rects + ((size_t)t * a.K + k) * 4;
-                rx1[k] = rc[0]; ry1[k] = rc[1]; rx2[k] = rc[2]; ry2[k] = rc[3];
-                hit[k] = rx1[k] < x1 && rx2[k] > x0 && ry1[k] < y1 && ry2[k] > y0 && rx2[k] > rx1[k] && ry2[k] > ry1[k];
+                tl.rx1[k] = rc[0]; tl.ry1[k] = rc[1]; tl.rx2[k] = rc[2]; tl.ry2[k] = rc[3];
+                tl.hit[k] = rc[0] < x1 && rc[2] > x0 && rc[1] < y1 && rc[3] > y0 && rc[2] > rc[0] && rc[3] > rc[1];
+                any_hit |= tl.hit[k];
             }
         }
+    }
+    // storage index of level-1 column (x0/2 - 1): the first thread's pair (J-1, J)
+    const int colofs_base = ((x0 >> 1) - 1) - g[1].co;
+    const bool edge = (x0 == 0) || ((x0 + a.TW) >> 1) + 1 >= a.w[1];
+    const bool vec = a.vec_ok && (x0 + a.TW <= a.W);
+    if (vec) {
+        if (any_hit) { if (edge) tl.template run<true, true, true>(colofs_base); else tl.template run<false, true, true>(colofs_base); }
+        else { if (edge) tl.template run<true, false, true>(colofs_base); else tl.template run<false, false, true>(colofs_base); }
+    } else {
+        if (any_hit) tl.template run<true, true, false>(colofs_base); else tl.template run<true, false, false>(colofs_base);
     }
 
-    float hm1[4], h0[4], hp1[4];
-    {
-        const int m0 = y0 >> 1;
-        const Tap3 tv = up_taps(y0, n1h);           // y0 is even: taps (m0-1 | 1, m0, m0+1 | n-1)
-        hrow(tv.i0, hm1);
-        hrow(tv.i1, h0);
-        hrow(tv.i2, hp1);
-        (void)m0;
-    }
-    const size_t row_elems = (size_t)a.W * 3;
-    size_t gofs = ((size_t)t * a.H + y0) * row_elems + (size_t)x0 * 3 + fbase;
-    for (int y = y0; y < y1; ++y, gofs += row_elems) {
-        if ((y & 1) == 0 && y != y0) {
-            // advance the window: m -> m+1
-            const int m = y >> 1;
+    if (KMAX > 0 && any_hit) {       // block-uniform
+        const int lane = tid & 31, wid = tid >> 5;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { hm1[j] = h0[j]; h0[j] = hp1[j]; }
-            hrow((m + 1 >= n1h) ? n1h - 1 : m + 1, hp1);
-        }
-        if (!any_valid) continue;
-        // original pixels -> float (magic-number conversion: 0x4B0000xx = 2^23 + xx)
-        uint32_t pw;
-        if (a.vec_ok && all_valid) {
-            pw = __ldg(reinterpret_cast<const uint32_t*>(a.frames + gofs));
-        } else {
-            pw = 0;
+        for (int k = 0; k < KMAX; ++k) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (gx[j] < x1) pw |= (uint32_t)__ldg(a.frames + gofs + j) << (8 * j);
-        }
-        float o[4];
+            for (int c = 0; c < 3; ++c) {
+                float v = tl.acc[k][c];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float f = __uint_as_float(__byte_perm(pw, 0x4B000000u, 0x7440 + j)) - 8388608.0f;
-            o[j] = (y & 1) ? fmaf(h0[j] + hp1[j], 0.5f, f)
-                           : fmaf(h0[j], 0.75f, fmaf(hm1[j] + hp1[j], 0.125f, f));
-        }
-        if (F32OUT) {
-            if (a.vec_ok && all_valid) {
-                *reinterpret_cast<float4*>(a.out_f32 + gofs) = make_float4(o[0], o[1], o[2], o[3]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (gx[j] < x1) a.out_f32[gofs + j] = o[j];
+                for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                if (lane == 0) red[wid][k][c] = v;
             }
         }
-        if (U8OUT) {
-            uint32_t q = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float v = fminf(fmaxf(o[j], 0.0f), 255.0f);
-                q |= (uint32_t)(int)(v + 0.5f) << (8 * j);
-            }
-            if (a.vec_ok && all_valid) {
-                *reinterpret_cast<uint32_t*>(a.out_u8 + gofs) = q;
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (gx[j] < x1) a.out_u8[gofs + j] = (uint8_t)(q >> (8 * j));
-            }
-        }
-        if (KMAX > 0) {
-#pragma unroll
-            for (int k = 0; k < KMAX; ++k) {
-                if (hit[k] && y >= ry1[k] && y < ry2[k]) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (gx[j] >= rx1[k] && gx[j] < rx2[k] && gx[j] < x1) acc[k][j] += o[j];
-                }
-            }
-        }
-    }
-
-    if (KMAX > 0) {
-        bool any_hit = false;
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k) any_hit |= hit[k];
-        if (any_hit) {       // block-uniform
-            const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-            for (int k = 0; k < KMAX; ++k) {
-                float s[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    s[0] += (ch[j] == 0) ? acc[k][j] : 0.f;
-                    s[1] += (ch[j] == 1) ? acc[k][j] : 0.f;
-                    s[2] += (ch[j] == 2) ? acc[k][j] : 0.f;
-                }
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    float v = s[c];
-#pragma unroll
-                    for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-                    if (lane == 0) red[wid][k][c] = v;
-                }
-            }
-            __syncthreads();
-            if (threadIdx.x < a.K * 3) {
-                const int k = threadIdx.x / 3, c = threadIdx.x - 3 * k;
-                double s = 0.0;
-                for (int w = 0; w < NTL / 32; ++w) s += (double)red[w][k][c];
-                a.partial[(((size_t)t * tiles + tile) * a.K + k) * 3 + c] = s;
-            }
+        __syncthreads();
+        if (tid < a.K * 3) {
+            const int k = tid / 3, c = tid - 3 * k;
+            double s = 0.0;
+            for (int w = 0; w < (nthreads + 31) / 32; ++w) s += (double)red[w][k][c];
+            a.partial[(((size_t)t * tiles + tile) * a.K + k) * 3 + c] = s;
         }
     }
 }
 
 // fixed-order reduction of the per-tile partials over the tiles a rectangle touches
 __global__ void roi_finalize_kernel(const double* __restrict__ partial, const int32_t* __restrict__ rects,
-                                    int T, int K, int tiles_x, int tiles_y, double* __restrict__ mean) {
+                                    int T, int K, int TW, int tiles_x, int tiles_y, double* __restrict__ mean) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= T * K * 3) return;
     const int c = idx % 3, k = (idx / 3) % K, t = idx / (3 * K);
@@ -302,13 +345,14 @@ __global__ void roi_finalize_kernel(const double* __restrict__ partial, const in
 }
 
 template <int KMAX>
-int launch_collapse(vhr_ctx* ctx, const ColArgs& a, size_t smem, cudaStream_t stream) {
+int launch_collapse(vhr_ctx* ctx, const ColArgs& a, dim3 block, size_t smem, cudaStream_t stream) {
     const unsigned grid = (unsigned)((size_t)a.T * a.tiles_x * a.tiles_y);
 #define VHR_COLLAPSE_LAUNCH(F, U)                                                                             \
     do {                                                                                                      \
         auto kern = collapse_kernel<KMAX, F, U>;                                                              \
         VHR_CHECK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        kern<<<grid, NTL, smem, stream>>>(a);                                                                  \
+        VHR_CHECK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
+        kern<<<grid, block, smem, stream>>>(a);                                                               \
     } while (0)
     if (a.out_f32 && a.out_u8) VHR_COLLAPSE_LAUNCH(true, true);
     else if (a.out_f32) VHR_COLLAPSE_LAUNCH(true, false);
@@ -337,23 +381,39 @@ extern "C" int vhr_collapse_addback_roi(vhr_ctx* ctx, const float* d_level, cons
     a.T = T; a.H = H; a.W = W; a.L = levels;
     PyrDims d = vhr_make_dims(W, H, levels);
     for (int l = 0; l <= VHR_MAX_LEVELS; ++l) { a.w[l] = d.w[l]; a.h[l] = d.h[l]; }
+    // tile width: the largest of 640/512/384/256/128 that divides W, else 256 (last tile partial)
+    int TW = 256;
+    const int cand[5] = {640, 512, 384, 256, 128};
+    for (int i = 0; i < 5; ++i)
+        if (W % cand[i] == 0) { TW = cand[i]; break; }
+    if (W < 256) TW = ((W + 127) / 128) * 128;
+    a.TW = TW;
     a.tiles_x = (W + TW - 1) / TW;
     a.tiles_y = (H + TH - 1) / TH;
+    const int cg = TW / 4;                              // thread columns (multiple of 32)
+    int rg = MAXT / cg;                                 // row-pair groups
+    if (rg < 1) rg = 1;
+    if (rg > TH / 2) rg = TH / 2;
+    dim3 block(cg, rg);
     a.rects = d_rects; a.K = K;
-    // shared-memory budget: odd levels share one buffer, even levels the other
+    // shared-memory budget: odd levels share one buffer, even levels the other (planar x3)
     size_t odd = 0, even = 0;
     {
         int rh = TH, rw = TW;
         for (int l = 1; l <= levels; ++l) {
-            rh = (rh - 1) / 2 + 4;      // rows (rb>>1)+1 - ((ra>>1)-1) + 1 of an rh-row region
-            rw = (rw - 1) / 2 + 4;
-            size_t n = (size_t)rh * rw * 3;
+            rh = rh / 2 + 5;
+            rw = rw / 2 + 10;
+            const size_t n = (size_t)3 * rh * rw;
             if (l & 1) odd = odd > n ? odd : n; else even = even > n ? even : n;
         }
     }
     a.buf_odd_off = 0;
     a.buf_even_off = (int)((odd + 3) & ~(size_t)3);
     const size_t smem = ((size_t)a.buf_even_off + even) * sizeof(float);
+    if ((long long)smem > ctx->smem_optin) {
+        vhr_set_error(ctx, "collapse: tile needs %zu bytes of shared memory (> %d)", smem, ctx->smem_optin);
+        return VHR_ERR_UNSUPPORTED;
+    }
     a.vec_ok = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_frames) & 3) == 0) &&
                (!d_out_f32 || (reinterpret_cast<uintptr_t>(d_out_f32) & 15) == 0) &&
                (!d_out_u8 || (reinterpret_cast<uintptr_t>(d_out_u8) & 3) == 0);
@@ -363,11 +423,11 @@ extern "C" int vhr_collapse_addback_roi(vhr_ctx* ctx, const float* d_level, cons
         if (rc != VHR_OK) return rc;
         a.partial = reinterpret_cast<double*>(p);
     }
-    int rc = (K > 0) ? launch_collapse<KMAXF>(ctx, a, smem, stream) : launch_collapse<0>(ctx, a, smem, stream);
+    int rc = (K > 0) ? launch_collapse<KMAXF>(ctx, a, block, smem, stream) : launch_collapse<0>(ctx, a, block, smem, stream);
     if (rc != VHR_OK) return rc;
     if (K > 0) {
         const int n = T * K * 3;
-        roi_finalize_kernel<<<(n + 127) / 128, 128, 0, stream>>>(a.partial, d_rects, T, K, a.tiles_x, a.tiles_y, d_roi_mean);
+        roi_finalize_kernel<<<(n + 127) / 128, 128, 0, stream>>>(a.partial, d_rects, T, K, TW, a.tiles_x, a.tiles_y, d_roi_mean);
         rc = vhr_after_launch(ctx, "roi_finalize_kernel");
     }
     return rc;
