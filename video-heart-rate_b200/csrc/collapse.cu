@@ -8,32 +8,37 @@
 // (rppg_VIDEO.py:60-66,106-110) evaluated on the magnified frame.
 //
 // Design (DESIGN.md "collapse"): this kernel moves 15 of the 18 bytes per pixel of the whole
-// EVM path (3 B/px read, 12 B/px written) and was instruction-bound in its first form, so it
-// is organised to minimise instructions per output value:
-//   * CTA = one TW x 32 pixel tile of one frame.  The pyrUp halo is one sample per level, so
-//     the whole chain for a tile (level-L region of a few samples up to a level-1 region of
-//     (TW/2+6) x 20) is rebuilt in shared memory; levels 1..L-1 never touch HBM.  Levels are
-//     stored PLANAR (channel planes) and each expansion step maps one thread to one source
-//     cell producing its 2x2 destination block (27 loads -> 12 values).
+// EVM path (3 B/px read, 12 B/px written).  Its first two forms were instruction-bound, so
+// everything here is organised to minimise instructions per output value and to make every
+// global store a full, contiguous 512-byte warp transaction:
+//   * CTA = one TW x TH pixel tile of one frame.  The pyrUp halo is one sample per level, so
+//     the chain for a tile (a few level-L samples up to a (TW/2+2) x (TH/2+2) level-1 region)
+//     is rebuilt in shared memory; levels 1..L-1 never touch HBM.
+//   * Regions are stored PLANAR (one plane per channel) with a one-sample APRON that holds
+//     the border-mapped neighbours (reflect-101 low / replicate high), written explicitly
+//     after each level is built.  Every stencil after that is a plain 3-tap with no index
+//     mapping, and each expansion is two separable, float4-vectorised passes
+//     (horizontal: 4 loads -> 4 values; vertical: 3 float4 loads -> 2 x 4 values).
 //   * Last expansion: one work item = 4 pixels x 2 rows (24 values): 18 LDS.64 from the
 //     level-1 planes, vertical then horizontal interpolation in registers, uint8 -> float by
-//     byte-permute + one add, add-back fused into the last FMA, three 16-byte stores per row.
-//     No sliding window: items are independent, registers stay low, occupancy high.
-//   * Frame-border fix-ups (reflect/replicate) and the ROI accumulation are compiled as
-//     separate loop bodies selected by block-uniform flags, so interior tiles pay for neither.
+//     byte-permute + one add, add-back fused into the last FMA.  Items are independent (no
+//     sliding window), so registers stay low and occupancy high.
+//   * Stores: a thread's 12 floats are 48 bytes, so direct float4 stores would write
+//     half-sectors at a 48-byte lane stride.  Each warp instead transposes a row segment
+//     (1536 B) through a private shared-memory strip and issues three fully coalesced STG.128.
 //   * ROI sums: per-thread float accumulators -> warp shuffle -> per-tile partial (double)
 //     -> fixed-order finalize kernel.  No atomics: results are run-to-run identical.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
-constexpr int TH = 32;                  // tile height (rows); even
-constexpr int MAXT = 320;               // max threads per CTA
+constexpr int MAXT = 256;               // max threads per CTA
 constexpr int KMAXF = 4;                // fused ROI rectangles per call
 
-struct LevelGeom {            // storage geometry of one level's region in shared memory
-    int ro, co;               // image row / col stored at index 0
-    int rs, ps;               // row stride, plane stride (floats)
+struct Geo {                  // storage of one level's region: planar, apron of >= 1 sample
+    int c0, r0;               // image col / row stored at index 0
+    int rs, ps;               // row stride, plane stride (floats; rs % 4 == 0)
     int off;                  // float offset of plane 0 in dynamic smem
 };
 
@@ -45,48 +50,96 @@ struct ColArgs {
     int T, H, W, L;
     int w[VHR_MAX_LEVELS + 1];
     int h[VHR_MAX_LEVELS + 1];
-    int TW;                   // tile width in pixels (multiple of 128)
+    int TW, TH;               // tile size in pixels (TW multiple of 128, TH even)
     int tiles_x, tiles_y;
     const int32_t* rects;     // (T,K,4)
     int K;
     double* partial;          // (T, tiles_y*tiles_x, K, 3)
-    int buf_odd_off, buf_even_off;   // float offsets into dynamic smem
+    int bufX_off, bufY_off, bufH_off, stage_off;   // float offsets into dynamic smem
     int vec_ok;               // W % 4 == 0 and bases aligned
 };
 
-// border-mapped neighbours of source index p on an axis of length n (cv2.pyrUp rule)
-__device__ __forceinline__ int nb_lo(int p, int n) { return (p - 1 < 0) ? (n > 1 ? 1 : 0) : p - 1; }
-__device__ __forceinline__ int nb_hi(int p, int n) { return (p + 1 >= n) ? n - 1 : p + 1; }
+__device__ __forceinline__ int border_map(int x, int n) { return x < 0 ? (n > 1 ? 1 : 0) : (x >= n ? n - 1 : x); }
 
-// one expansion step in shared memory: every source cell (p,i) of level l+1 produces the 2x2
-// destination block (2p..2p+1, 2i..2i+1) of level l, all three channel planes.
-__device__ __forceinline__ void expand_level(const float* __restrict__ smf, const LevelGeom& s, int sn_h, int sn_w,
-                                             float* __restrict__ smw, const LevelGeom& d, int p_lo, int p_hi,
-                                             int i_lo, int i_hi, int tid, int nthreads) {
-    const int ni = i_hi - i_lo + 1;
-    const int ncell = (p_hi - p_lo + 1) * ni;
-    for (int cell = tid; cell < ncell; cell += nthreads) {
-        const int pr = cell / ni;
-        const int p = p_lo + pr, i = i_lo + (cell - pr * ni);
-        const int r0 = (nb_lo(p, sn_h) - s.ro) * s.rs, r1 = (min(p, sn_h - 1) - s.ro) * s.rs, r2 = (nb_hi(p, sn_h) - s.ro) * s.rs;
-        const int c0 = nb_lo(i, sn_w) - s.co, c1 = min(i, sn_w - 1) - s.co, c2 = nb_hi(i, sn_w) - s.co;
-        const int dbase = (2 * p - d.ro) * d.rs + (2 * i - d.co);
+// Horizontal expansion (pass A): rows p_lo..p_hi of source level (stored in S, aprons valid)
+// -> Hh rows (same row indexing as S) at destination column resolution, column groups
+// g_lo..g_hi, group g = destination columns 4g-1 .. 4g+2 (stored 16-byte aligned).
+__device__ __forceinline__ void expand_h(float* __restrict__ sm, const Geo S, const Geo Hh, int p_lo, int p_hi,
+                                         int g_lo, int g_hi, int tid, int nthreads) {
+    const int ng = g_hi - g_lo + 1;
+    const int n = (p_hi - p_lo + 1) * ng;
+    const unsigned inv = 0xFFFFFFFFu / (unsigned)ng + 1u;       // it / ng == umulhi(it, inv) for it < 65536
+    for (int it = tid; it < n; it += nthreads) {
+        const int pr = (int)__umulhi((unsigned)it, inv);
+        const int g = g_lo + (it - pr * ng), p = p_lo + pr;
+        const int so = (p - S.r0) * S.rs + (2 * g - 1 - S.c0);
+        const int ho = (p - Hh.r0) * Hh.rs + (4 * g - 1 - Hh.c0);
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
-            const float* sp = smf + s.off + ch * s.ps;
-            float he[3], ho[3];
-            const int rr[3] = {r0, r1, r2};
+            const float* sp = sm + S.off + ch * S.ps + so;
+            const float x0 = sp[0], x1 = sp[1], x2 = sp[2], x3 = sp[3];
+            float4 o;
+            o.x = (x0 + x1) * 0.5f;                          // col 4g-1 (odd,  i = 2g-1)
+            o.y = fmaf(x0 + x2, 0.125f, x1 * 0.75f);         // col 4g   (even, i = 2g)
+            o.z = (x1 + x2) * 0.5f;                          // col 4g+1
+            o.w = fmaf(x1 + x3, 0.125f, x2 * 0.75f);         // col 4g+2 (even, i = 2g+1)
+            *reinterpret_cast<float4*>(sm + Hh.off + ch * Hh.ps + ho) = o;
+        }
+    }
+}
+
+// Vertical expansion (pass B): Hh rows p-1, p, p+1 -> destination rows 2p, 2p+1.
+__device__ __forceinline__ void expand_v(float* __restrict__ sm, const Geo Hh, const Geo D, int p_lo, int p_hi,
+                                         int g_lo, int g_hi, int tid, int nthreads) {
+    const int ng = g_hi - g_lo + 1;
+    const int n = (p_hi - p_lo + 1) * ng;
+    const unsigned inv = 0xFFFFFFFFu / (unsigned)ng + 1u;
+    for (int it = tid; it < n; it += nthreads) {
+        const int pr = (int)__umulhi((unsigned)it, inv);
+        const int g = g_lo + (it - pr * ng), p = p_lo + pr;
+        const int ho = (p - Hh.r0) * Hh.rs + (4 * g - 1 - Hh.c0);
+        const int dofs = (2 * p - D.r0) * D.rs + (4 * g - 1 - D.c0);
 #pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                const float x0 = sp[rr[q] + c0], x1 = sp[rr[q] + c1], x2 = sp[rr[q] + c2];
-                he[q] = fmaf(x0 + x2, 0.125f, x1 * 0.75f);
-                ho[q] = (x1 + x2) * 0.5f;
-            }
-            float* dp = smw + d.off + ch * d.ps + dbase;
-            dp[0] = fmaf(he[0] + he[2], 0.125f, he[1] * 0.75f);
-            dp[1] = fmaf(ho[0] + ho[2], 0.125f, ho[1] * 0.75f);
-            dp[d.rs] = (he[1] + he[2]) * 0.5f;
-            dp[d.rs + 1] = (ho[1] + ho[2]) * 0.5f;
+        for (int ch = 0; ch < 3; ++ch) {
+            const float* hp = sm + Hh.off + ch * Hh.ps + ho;
+            const float4 a = *reinterpret_cast<const float4*>(hp - Hh.rs);
+            const float4 b = *reinterpret_cast<const float4*>(hp);
+            const float4 c = *reinterpret_cast<const float4*>(hp + Hh.rs);
+            float4 e, o;
+            e.x = fmaf(a.x + c.x, 0.125f, b.x * 0.75f); o.x = (b.x + c.x) * 0.5f;
+            e.y = fmaf(a.y + c.y, 0.125f, b.y * 0.75f); o.y = (b.y + c.y) * 0.5f;
+            e.z = fmaf(a.z + c.z, 0.125f, b.z * 0.75f); o.z = (b.z + c.z) * 0.5f;
+            e.w = fmaf(a.w + c.w, 0.125f, b.w * 0.75f); o.w = (b.w + c.w) * 0.5f;
+            float* dp = sm + D.off + ch * D.ps + dofs;
+            *reinterpret_cast<float4*>(dp) = e;
+            *reinterpret_cast<float4*>(dp + D.rs) = o;
+        }
+    }
+}
+
+// Write the apron of a freshly built region where the tile touches the image border:
+// column -1 := column 1 (reflect-101), column n := column n-1 (replicate); then the same for
+// rows (whole stored rows, aprons included).  Block-uniform conditions.
+__device__ __forceinline__ void fix_aprons(float* __restrict__ sm, const Geo D, int ra, int rb, int ca, int cb,
+                                           int nh, int nw, int tid, int nthreads) {
+    const bool left = (ca == 0), right = (cb == nw - 1), top = (ra == 0), bot = (rb == nh - 1);
+    if (left || right) {
+        const int nr = rb - ra + 1;
+        for (int it = tid; it < nr * 3; it += nthreads) {
+            const int ch = it / nr, r = ra + (it - ch * nr);
+            float* row = sm + D.off + ch * D.ps + (r - D.r0) * D.rs - D.c0;
+            if (left) row[-1] = row[nw > 1 ? 1 : 0];
+            if (right) row[nw] = row[nw - 1];
+        }
+    }
+    if (top || bot) {
+        __syncthreads();
+        const int c_lo = ca - 1, ncol = cb - ca + 3;
+        for (int it = tid; it < ncol * 3; it += nthreads) {
+            const int ch = it / ncol, c = c_lo + (it - ch * ncol);
+            float* col = sm + D.off + ch * D.ps + (c - D.c0) - D.r0 * D.rs;
+            if (top) col[-1 * D.rs] = col[(nh > 1 ? 1 : 0) * D.rs];
+            if (bot) col[nh * D.rs] = col[(nh - 1) * D.rs];
         }
     }
 }
@@ -95,89 +148,111 @@ template <int KMAX, bool F32OUT, bool U8OUT>
 struct Tile {
     const ColArgs& a;
     int t, x0, x1, y0, y1;
-    // level-1 geometry
-    const float* l1;
-    int l1_rs, l1_ps, l1_ro;
-    int n1w, n1h;
-    // ROI (block-uniform)
+    const float* l1;          // level-1 plane 0, pre-offset so that l1[r * rs + c] = value(row r, col c)
+    int l1_rs, l1_ps;
+    float* stage;             // this warp's 1536-byte transpose strip
     int rx1[KMAXF > 0 ? KMAXF : 1], ry1[KMAXF > 0 ? KMAXF : 1], rx2[KMAXF > 0 ? KMAXF : 1], ry2[KMAXF > 0 ? KMAXF : 1];
     bool hit[KMAXF > 0 ? KMAXF : 1];
     float acc[KMAXF > 0 ? KMAXF : 1][3];
 
     __device__ Tile(const ColArgs& a_) : a(a_) {}
 
-    // one work item: pixels X..X+3, rows 2m and 2m+1
-    template <bool EDGE, bool ROI, bool VEC>
-    __device__ __forceinline__ void item(int X, int m, int colofs) {
-        const int rm = (nb_lo(m, n1h) - l1_ro) * l1_rs, rc = (m - l1_ro) * l1_rs, rp = (nb_hi(m, n1h) - l1_ro) * l1_rs;
+    // one work item: pixels X..X+3, rows 2m and 2m+1.  `active` is false for lanes right of
+    // the tile's valid width (they still take part in the warp-wide store transpose).
+    template <bool ROI, bool VEC>
+    __device__ __forceinline__ void item(int X, int m, bool active, int warp_X0) {
         float ve[3][4], vo[3][4];
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            const float* pl = l1 + ch * l1_ps + colofs;
-            const float2 a0 = *reinterpret_cast<const float2*>(pl + rm), a1 = *reinterpret_cast<const float2*>(pl + rm + 2);
-            const float2 b0 = *reinterpret_cast<const float2*>(pl + rc), b1 = *reinterpret_cast<const float2*>(pl + rc + 2);
-            const float2 c0 = *reinterpret_cast<const float2*>(pl + rp), c1 = *reinterpret_cast<const float2*>(pl + rp + 2);
-            const float av[4] = {a0.x, a0.y, a1.x, a1.y}, bv[4] = {b0.x, b0.y, b1.x, b1.y}, cv[4] = {c0.x, c0.y, c1.x, c1.y};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                ve[ch][j] = fmaf(av[j] + cv[j], 0.125f, bv[j] * 0.75f);
-                vo[ch][j] = (bv[j] + cv[j]) * 0.5f;
-            }
-            if (EDGE) {
-                const int J = X >> 1;
-                if (J + 1 >= n1w) { ve[ch][2] = ve[ch][1]; vo[ch][2] = vo[ch][1]; }           // replicate high side
-                if (J + 2 >= n1w) { ve[ch][3] = ve[ch][2]; vo[ch][3] = vo[ch][2]; }
-                if (J - 1 < 0) { ve[ch][0] = ve[ch][2]; vo[ch][0] = vo[ch][2]; }              // reflect-101: col -1 -> col 1
+        const size_t row_elems = (size_t)a.W * 3;
+        const size_t g0 = ((size_t)t * a.H + 2 * m) * row_elems + (size_t)X * 3;
+        uint32_t wq[2][3];
+        if (VEC && active) {                          // both rows' pixels in flight before any shared-memory work
+            const uint32_t* fp = reinterpret_cast<const uint32_t*>(a.frames + g0);
+            wq[0][0] = __ldg(fp); wq[0][1] = __ldg(fp + 1); wq[0][2] = __ldg(fp + 2);
+            if (2 * m + 1 < y1) {
+                const uint32_t* fq = reinterpret_cast<const uint32_t*>(a.frames + g0 + row_elems);
+                wq[1][0] = __ldg(fq); wq[1][1] = __ldg(fq + 1); wq[1][2] = __ldg(fq + 2);
             }
         }
-        const size_t row_elems = (size_t)a.W * 3;
+        if (active) {
+            const int J = X >> 1;
+            const float* pl0 = l1 + (m - 1) * l1_rs + (J - 1);
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const float* pl = pl0 + ch * l1_ps;
+                const float2 a0 = *reinterpret_cast<const float2*>(pl), a1 = *reinterpret_cast<const float2*>(pl + 2);
+                const float2 b0 = *reinterpret_cast<const float2*>(pl + l1_rs), b1 = *reinterpret_cast<const float2*>(pl + l1_rs + 2);
+                const float2 c0 = *reinterpret_cast<const float2*>(pl + 2 * l1_rs), c1 = *reinterpret_cast<const float2*>(pl + 2 * l1_rs + 2);
+                const float av[4] = {a0.x, a0.y, a1.x, a1.y}, bv[4] = {b0.x, b0.y, b1.x, b1.y}, cv[4] = {c0.x, c0.y, c1.x, c1.y};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    ve[ch][j] = fmaf(av[j] + cv[j], 0.125f, bv[j] * 0.75f);
+                    vo[ch][j] = (bv[j] + cv[j]) * 0.5f;
+                }
+            }
+        }
+        const int lane = threadIdx.x & 31;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             const int y = 2 * m + half;
-            if (y < y0 || y >= y1) continue;          // tile rows start even; only the frame's last odd row can be cut
-            const size_t g = ((size_t)t * a.H + y) * row_elems + (size_t)X * 3;
-            uint32_t w0, w1, w2;
-            if (VEC) {
-                const uint32_t* fp = reinterpret_cast<const uint32_t*>(a.frames + g);
-                w0 = __ldg(fp); w1 = __ldg(fp + 1); w2 = __ldg(fp + 2);
-            } else {
-                w0 = w1 = w2 = 0;
+            if (y >= y1) continue;                    // warp-uniform (only the frame's last odd row can be cut)
+            const size_t g = g0 + (half ? row_elems : 0);
+            const size_t grow = g - (size_t)X * 3;
+            float o[12];
+            if (active) {
+                uint32_t w0, w1, w2;
+                if (VEC) {
+                    w0 = wq[half][0]; w1 = wq[half][1]; w2 = wq[half][2];
+                } else {
+                    w0 = w1 = w2 = 0;
 #pragma unroll
-                for (int k = 0; k < 12; ++k) {
-                    if (X + k / 3 < x1) {
-                        const uint32_t bv = __ldg(a.frames + g + k);
-                        if (k < 4) w0 |= bv << (8 * k); else if (k < 8) w1 |= bv << (8 * (k - 4)); else w2 |= bv << (8 * (k - 8));
+                    for (int k = 0; k < 12; ++k) {
+                        if (X + k / 3 < x1) {
+                            const uint32_t bv = __ldg(a.frames + g + k);
+                            if (k < 4) w0 |= bv << (8 * k); else if (k < 8) w1 |= bv << (8 * (k - 4)); else w2 |= bv << (8 * (k - 8));
+                        }
                     }
                 }
-            }
-            const uint32_t ww[3] = {w0, w1, w2};
-            float o[12];
+                const uint32_t ww[3] = {w0, w1, w2};
 #pragma unroll
-            for (int k = 0; k < 12; ++k) {
-                const int px = k / 3, ch = k - 3 * px;
-                // uint8 -> float: 0x4B0000xx = 2^23 + xx
-                const float f = __uint_as_float(__byte_perm(ww[k >> 2], 0x4B000000u, 0x7440 + (k & 3))) - 8388608.0f;
-                const float (&v)[4] = half ? vo[ch] : ve[ch];
-                float up;
-                if (px == 0) up = fmaf(v[0] + v[2], 0.125f, fmaf(v[1], 0.75f, f));
-                else if (px == 1) up = fmaf(v[1] + v[2], 0.5f, f);
-                else if (px == 2) up = fmaf(v[1] + v[3], 0.125f, fmaf(v[2], 0.75f, f));
-                else up = fmaf(v[2] + v[3], 0.5f, f);
-                o[k] = up;
+                for (int k = 0; k < 12; ++k) {
+                    const int px = k / 3, ch = k - 3 * px;
+                    // uint8 -> float: 0x4B0000xx = 2^23 + xx
+                    const float f = __uint_as_float(__byte_perm(ww[k >> 2], 0x4B000000u, 0x7440 + (k & 3))) - 8388608.0f;
+                    const float (&v)[4] = half ? vo[ch] : ve[ch];
+                    float up;
+                    if (px == 0) up = fmaf(v[0] + v[2], 0.125f, fmaf(v[1], 0.75f, f));
+                    else if (px == 1) up = fmaf(v[1] + v[2], 0.5f, f);
+                    else if (px == 2) up = fmaf(v[1] + v[3], 0.125f, fmaf(v[2], 0.75f, f));
+                    else up = fmaf(v[2] + v[3], 0.5f, f);
+                    o[k] = up;
+                }
             }
             if (F32OUT) {
                 if (VEC) {
-                    float4* op = reinterpret_cast<float4*>(a.out_f32 + g);
-                    op[0] = make_float4(o[0], o[1], o[2], o[3]);
-                    op[1] = make_float4(o[4], o[5], o[6], o[7]);
-                    op[2] = make_float4(o[8], o[9], o[10], o[11]);
-                } else {
+                    // transpose the warp's 32 x 48 B through its strip: conflict-free 16-byte
+                    // stores (lane stride 12 words), then three contiguous 512-byte warp stores
+                    if (active) {
+                        float4* sp = reinterpret_cast<float4*>(stage + 12 * lane);
+                        sp[0] = make_float4(o[0], o[1], o[2], o[3]);
+                        sp[1] = make_float4(o[4], o[5], o[6], o[7]);
+                        sp[2] = make_float4(o[8], o[9], o[10], o[11]);
+                    }
+                    __syncwarp();
+                    float* wout = a.out_f32 + grow + (size_t)warp_X0 * 3;
+                    const int nvalid = min(32, (x1 - warp_X0) >> 2) * 3;      // valid 16-byte chunks of this warp's segment
+#pragma unroll
+                    for (int s = 0; s < 3; ++s) {
+                        const int c = s * 32 + lane;
+                        if (c < nvalid) *reinterpret_cast<float4*>(wout + 4 * c) = *reinterpret_cast<const float4*>(stage + 4 * c);
+                    }
+                    __syncwarp();
+                } else if (active) {
 #pragma unroll
                     for (int k = 0; k < 12; ++k)
                         if (X + k / 3 < x1) a.out_f32[g + k] = o[k];
                 }
             }
-            if (U8OUT) {
+            if (U8OUT && active) {
                 uint32_t q[3] = {0, 0, 0};
 #pragma unroll
                 for (int k = 0; k < 12; ++k) {
@@ -193,7 +268,7 @@ struct Tile {
                         if (X + k / 3 < x1) a.out_u8[g + k] = (uint8_t)(q[k >> 2] >> (8 * (k & 3)));
                 }
             }
-            if (ROI && KMAX > 0) {
+            if (ROI && KMAX > 0 && active) {
 #pragma unroll
                 for (int k = 0; k < KMAX; ++k) {
                     if (hit[k] && y >= ry1[k] && y < ry2[k]) {
@@ -209,12 +284,13 @@ struct Tile {
         }
     }
 
-    template <bool EDGE, bool ROI, bool VEC>
-    __device__ __forceinline__ void run(int colofs_base) {
-        const int cx = threadIdx.x, X = x0 + 4 * cx;
-        if (X >= x1) return;
-        const int colofs = colofs_base + 2 * cx;
-        for (int m = (y0 >> 1) + threadIdx.y; 2 * m < y1; m += blockDim.y) item<EDGE, ROI, VEC>(X, m, colofs);
+    template <bool ROI, bool VEC>
+    __device__ __forceinline__ void run() {
+        const int X = x0 + 4 * threadIdx.x;
+        const int warp_X0 = x0 + 4 * (threadIdx.x & ~31);
+        if (warp_X0 >= x1) return;                   // whole warp right of the image
+        const bool active = X < x1;
+        for (int m = (y0 >> 1) + threadIdx.y; 2 * m < y1; m += blockDim.y) item<ROI, VEC>(X, m, active, warp_X0);
     }
 };
 
@@ -230,53 +306,75 @@ __global__ void __launch_bounds__(MAXT, 3) collapse_kernel(const ColArgs a) {
     const int tile = blockIdx.x - t * tiles;
     const int by = tile / a.tiles_x, bx = tile - by * a.tiles_x;
     const int x0 = bx * a.TW, x1 = min(a.W, x0 + a.TW);
-    const int y0 = by * TH, y1 = min(a.H, y0 + TH);
+    const int y0 = by * a.TH, y1 = min(a.H, y0 + a.TH);
     const int L = a.L;
 
-    // regions [ra,rb] x [ca,cb] needed at each level (inclusive) and their smem storage
-    int ra[VHR_MAX_LEVELS + 1], rb[VHR_MAX_LEVELS + 1], ca[VHR_MAX_LEVELS + 1], cb[VHR_MAX_LEVELS + 1];
-    LevelGeom g[VHR_MAX_LEVELS + 1];
-    ra[0] = y0; rb[0] = y1 - 1; ca[0] = x0; cb[0] = x0 + a.TW - 1;   // full tile width: partial tiles still index within it
-    for (int l = 1; l <= L; ++l) {
-        ra[l] = max(0, (ra[l - 1] >> 1) - 1);
-        rb[l] = min(a.h[l] - 1, (rb[l - 1] >> 1) + 1);
-        ca[l] = max(0, (ca[l - 1] >> 1) - 1);
-        cb[l] = min(a.w[l] - 1, (cb[l - 1] >> 1) + 1);
-        if (cb[l] < ca[l]) cb[l] = ca[l];            // partial tile far right of a tiny level
-        LevelGeom& q = g[l];
-        q.ro = ra[l] & ~1;                            // 2x2 blocks start on even rows / cols
-        q.co = (ca[l] & ~1) - 1;                      // odd origin: the pairs (J-1,J) read by the last stage are 8-byte aligned
-        const int nrows = (rb[l] | 1) - q.ro + 1;
-        q.rs = (((cb[l] | 1) + 3 - q.co + 1) + 1) & ~1;       // +3: slack columns read (and discarded) at the frame edge
-        q.ps = nrows * q.rs;
-        q.off = (l & 1) ? a.buf_odd_off : a.buf_even_off;
-    }
-
-    // ---- level L region from HBM (interleaved) into planar smem ---------------------------
-    {
-        const LevelGeom& q = g[L];
-        const int rw = (cb[L] - ca[L] + 1) * 3, rh = rb[L] - ra[L] + 1;
-        const float* src = a.lvl + ((size_t)t * a.h[L] * a.w[L]) * 3;
-        for (int idx = tid; idx < rw * rh; idx += nthreads) {
-            const int r = idx / rw, j = idx - r * rw;
-            const int c = j / 3, ch = j - 3 * c;
-            smf[q.off + ch * q.ps + (ra[L] + r - q.ro) * q.rs + (ca[L] + c - q.co)] =
-                __ldg(src + ((size_t)(ra[L] + r) * a.w[L] + ca[L]) * 3 + j);
+    // regions [ra,rb] x [ca,cb] (inclusive, inside the image) needed at each level and their
+    // storage geometry: computed once per tile by threads 1..L into shared memory (dynamically
+    // indexed per-thread arrays would live in local memory and be re-read in every loop)
+    __shared__ int s_reg[VHR_MAX_LEVELS + 1][4];       // ra, rb, ca, cb
+    __shared__ Geo s_geo[VHR_MAX_LEVELS + 1];
+    if (tid >= 1 && tid <= L) {
+        int ra = y0, rb = y1 - 1, ca = x0, cb = x1 - 1;
+        for (int l = 1; l <= tid; ++l) {
+            ra = max(0, (ra >> 1) - 1);
+            rb = min(a.h[l] - 1, (rb >> 1) + 1);
+            ca = max(0, (ca >> 1) - 1);
+            cb = min(a.w[l] - 1, (cb >> 1) + 1);
         }
-    }
-    // ---- levels L-1 .. 1 in shared memory ----------------------------------------------------
-    for (int l = L - 1; l >= 1; --l) {
-        __syncthreads();
-        expand_level(smf, g[l + 1], a.h[l + 1], a.w[l + 1], smf, g[l], g[l].ro >> 1, rb[l] >> 1, (g[l].co + 1) >> 1,
-                     cb[l] >> 1, tid, nthreads);
+        Geo q;
+        q.c0 = 4 * (ca >> 2) - 5;                     // column 4g-1 lands on an index that is a multiple of 4
+        q.r0 = ra - 2;
+        q.rs = ((cb + 8 - q.c0) + 3) & ~3;
+        q.ps = (rb - ra + 5) * q.rs;
+        q.off = 0;                                    // every level lives at offset 0 (lifetimes do not overlap)
+        s_geo[tid] = q;
+        s_reg[tid][0] = ra; s_reg[tid][1] = rb; s_reg[tid][2] = ca; s_reg[tid][3] = cb;
     }
     __syncthreads();
+
+    // ---- level L region (+ apron, border-mapped at load time) from HBM into planar smem ----
+    {
+        const Geo q = s_geo[L];
+        const int raL = s_reg[L][0], rbL = s_reg[L][1], caL = s_reg[L][2], cbL = s_reg[L][3];
+        const int nr = rbL - raL + 3, nc3 = (cbL - caL + 3) * 3;
+        const unsigned inv = 0xFFFFFFFFu / (unsigned)nc3 + 1u;
+        const float* src = a.lvl + ((size_t)t * a.h[L] * a.w[L]) * 3;
+        for (int idx = tid; idx < nr * nc3; idx += nthreads) {
+            const int r = (int)__umulhi((unsigned)idx, inv), j = idx - r * nc3;
+            const int c = (int)__umulhi((unsigned)j, 0x55555556u), ch = j - 3 * c;
+            const int ir = raL - 1 + r, ic = caL - 1 + c;
+            smf[q.off + ch * q.ps + (ir - q.r0) * q.rs + (ic - q.c0)] =
+                __ldg(src + ((size_t)border_map(ir, a.h[L]) * a.w[L] + border_map(ic, a.w[L])) * 3 + ch);
+        }
+    }
+    // ---- levels L-1 .. 1: separable expansion, aprons rewritten after each level ----------
+    for (int l = L - 1; l >= 1; --l) {
+        const Geo S = s_geo[l + 1], D = s_geo[l];
+        const int ral = s_reg[l][0], rbl = s_reg[l][1], cal = s_reg[l][2], cbl = s_reg[l][3];
+        Geo hh;                                       // H rows: source row indexing, destination column indexing
+        hh.c0 = D.c0; hh.rs = D.rs;
+        hh.r0 = S.r0;
+        hh.ps = (s_reg[l + 1][1] - s_reg[l + 1][0] + 5) * hh.rs;
+        hh.off = a.bufH_off;
+        const int g_lo = (cal + 1) >> 2, g_hi = (cbl + 1) >> 2;
+        const int p_lo = ral >> 1, p_hi = rbl >> 1;
+        __syncthreads();
+        expand_h(smf, S, hh, p_lo - 1, p_hi + 1, g_lo, g_hi, tid, nthreads);
+        __syncthreads();
+        expand_v(smf, hh, D, p_lo, p_hi, g_lo, g_hi, tid, nthreads);
+        __syncthreads();
+        fix_aprons(smf, D, ral, rbl, cal, cbl, a.h[l], a.w[l], tid, nthreads);
+    }
+    __syncthreads();
+    const Geo g1 = s_geo[1];
 
     // ---- last expansion fused with add-back, store and ROI sums -------------------------------
     Tile<KMAX, F32OUT, U8OUT> tl(a);
     tl.t = t; tl.x0 = x0; tl.x1 = x1; tl.y0 = y0; tl.y1 = y1;
-    tl.l1 = smf + g[1].off; tl.l1_rs = g[1].rs; tl.l1_ps = g[1].ps; tl.l1_ro = g[1].ro;
-    tl.n1w = a.w[1]; tl.n1h = a.h[1];
+    tl.l1 = smf + g1.off - g1.r0 * g1.rs - g1.c0;
+    tl.l1_rs = g1.rs; tl.l1_ps = g1.ps;
+    tl.stage = smf + a.stage_off + (tid >> 5) * 384;
     bool any_hit = false;
     if (KMAX > 0) {
 #pragma unroll
@@ -291,15 +389,10 @@ __global__ void __launch_bounds__(MAXT, 3) collapse_kernel(const ColArgs a) {
             }
         }
     }
-    // storage index of level-1 column (x0/2 - 1): the first thread's pair (J-1, J)
-    const int colofs_base = ((x0 >> 1) - 1) - g[1].co;
-    const bool edge = (x0 == 0) || ((x0 + a.TW) >> 1) + 1 >= a.w[1];
-    const bool vec = a.vec_ok && (x0 + a.TW <= a.W);
-    if (vec) {
-        if (any_hit) { if (edge) tl.template run<true, true, true>(colofs_base); else tl.template run<false, true, true>(colofs_base); }
-        else { if (edge) tl.template run<true, false, true>(colofs_base); else tl.template run<false, false, true>(colofs_base); }
+    if (a.vec_ok) {
+        if (any_hit) tl.template run<true, true>(); else tl.template run<false, true>();
     } else {
-        if (any_hit) tl.template run<true, true, false>(colofs_base); else tl.template run<true, false, false>(colofs_base);
+        if (any_hit) tl.template run<true, false>(); else tl.template run<false, false>();
     }
 
     if (KMAX > 0 && any_hit) {       // block-uniform
@@ -326,7 +419,7 @@ __global__ void __launch_bounds__(MAXT, 3) collapse_kernel(const ColArgs a) {
 
 // fixed-order reduction of the per-tile partials over the tiles a rectangle touches
 __global__ void roi_finalize_kernel(const double* __restrict__ partial, const int32_t* __restrict__ rects,
-                                    int T, int K, int TW, int tiles_x, int tiles_y, double* __restrict__ mean) {
+                                    int T, int K, int TW, int TH, int tiles_x, int tiles_y, double* __restrict__ mean) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= T * K * 3) return;
     const int c = idx % 3, k = (idx / 3) % K, t = idx / (3 * K);
@@ -381,13 +474,16 @@ extern "C" int vhr_collapse_addback_roi(vhr_ctx* ctx, const float* d_level, cons
     a.T = T; a.H = H; a.W = W; a.L = levels;
     PyrDims d = vhr_make_dims(W, H, levels);
     for (int l = 0; l <= VHR_MAX_LEVELS; ++l) { a.w[l] = d.w[l]; a.h[l] = d.h[l]; }
-    // tile width: the largest of 640/512/384/256/128 that divides W, else 256 (last tile partial)
-    int TW = 256;
-    const int cand[5] = {640, 512, 384, 256, 128};
-    for (int i = 0; i < 5; ++i)
-        if (W % cand[i] == 0) { TW = cand[i]; break; }
-    if (W < 256) TW = ((W + 127) / 128) * 128;
-    a.TW = TW;
+    // tile: 256 x 32 by default (three CTAs per SM); tunable for experiments
+    int TW = 256, TH = 32;
+    if (const char* e = getenv("VHR_COLLAPSE_TW")) TW = atoi(e);
+    if (const char* e = getenv("VHR_COLLAPSE_TH")) TH = atoi(e);
+    if (TW < 128 || TW % 128 != 0 || TW > 1024 || TH < 2 || TH % 2 != 0 || TH > 128) {
+        vhr_set_error(ctx, "collapse: bad tile %dx%d", TW, TH);
+        return VHR_ERR_INVALID;
+    }
+    if (W < TW) TW = ((W + 127) / 128) * 128;
+    a.TW = TW; a.TH = TH;
     a.tiles_x = (W + TW - 1) / TW;
     a.tiles_y = (H + TH - 1) / TH;
     const int cg = TW / 4;                              // thread columns (multiple of 32)
@@ -395,21 +491,33 @@ extern "C" int vhr_collapse_addback_roi(vhr_ctx* ctx, const float* d_level, cons
     if (rg < 1) rg = 1;
     if (rg > TH / 2) rg = TH / 2;
     dim3 block(cg, rg);
+    VHR_REQUIRE(ctx, cg * rg <= MAXT, "tile too wide for one CTA");
     a.rects = d_rects; a.K = K;
-    // shared-memory budget: odd levels share one buffer, even levels the other (planar x3)
-    size_t odd = 0, even = 0;
+    // shared memory: X = odd levels (level 1 is the largest), Y = even levels, H = pass-A rows
+    size_t szX = 0, szY = 0, szH = 0;
     {
         int rh = TH, rw = TW;
         for (int l = 1; l <= levels; ++l) {
-            rh = rh / 2 + 5;
-            rw = rw / 2 + 10;
-            const size_t n = (size_t)3 * rh * rw;
-            if (l & 1) odd = odd > n ? odd : n; else even = even > n ? even : n;
+            const int rh_src_rows = rh / 2 / 2 + 4 + 5;            // rows of level l+1 region (+ slack), for H
+            rh = rh / 2 + 3;                                      // rows rb-ra+1 of level l
+            rw = rw / 2 + 3;
+            const size_t rs = (size_t)((rw + 16 + 3) & ~3);
+            const size_t n = 3 * (size_t)(rh + 4) * rs;
+            if (l & 1) szX = szX > n ? szX : n; else szY = szY > n ? szY : n;
+            const size_t nh = 3 * (size_t)rh_src_rows * rs;
+            if (l < levels) szH = szH > nh ? szH : nh;
         }
     }
-    a.buf_odd_off = 0;
-    a.buf_even_off = (int)((odd + 3) & ~(size_t)3);
-    const size_t smem = ((size_t)a.buf_even_off + even) * sizeof(float);
+    // Lifetimes let the buffers overlap: a level is dead once pass A has turned it into H rows,
+    // and the next level is only written by pass B (a barrier later), so every level lives at
+    // offset 0; the store-transpose strips are only used after the last H is dead.
+    const size_t szR = szX > szY ? szX : szY;
+    const size_t szS = (size_t)((cg * rg + 31) / 32) * 384;
+    a.bufX_off = 0;
+    a.bufY_off = 0;
+    a.bufH_off = (int)((szR + 3) & ~(size_t)3);
+    a.stage_off = a.bufH_off;
+    const size_t smem = ((size_t)a.bufH_off + (szH > szS ? szH : szS)) * sizeof(float);
     if ((long long)smem > ctx->smem_optin) {
         vhr_set_error(ctx, "collapse: tile needs %zu bytes of shared memory (> %d)", smem, ctx->smem_optin);
         return VHR_ERR_UNSUPPORTED;
@@ -423,11 +531,13 @@ extern "C" int vhr_collapse_addback_roi(vhr_ctx* ctx, const float* d_level, cons
         if (rc != VHR_OK) return rc;
         a.partial = reinterpret_cast<double*>(p);
     }
-    int rc = (K > 0) ? launch_collapse<KMAXF>(ctx, a, block, smem, stream) : launch_collapse<0>(ctx, a, block, smem, stream);
+    int rc = (K == 0) ? launch_collapse<0>(ctx, a, block, smem, stream)
+           : (K == 1) ? launch_collapse<1>(ctx, a, block, smem, stream)
+                      : launch_collapse<KMAXF>(ctx, a, block, smem, stream);
     if (rc != VHR_OK) return rc;
     if (K > 0) {
         const int n = T * K * 3;
-        roi_finalize_kernel<<<(n + 127) / 128, 128, 0, stream>>>(a.partial, d_rects, T, K, TW, a.tiles_x, a.tiles_y, d_roi_mean);
+        roi_finalize_kernel<<<(n + 127) / 128, 128, 0, stream>>>(a.partial, d_rects, T, K, TW, TH, a.tiles_x, a.tiles_y, d_roi_mean);
         rc = vhr_after_launch(ctx, "roi_finalize_kernel");
     }
     return rc;
