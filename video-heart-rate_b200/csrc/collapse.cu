@@ -229,23 +229,30 @@ struct Tile {
             }
             if (F32OUT) {
                 if (VEC) {
-                    // transpose the warp's 32 x 48 B through its strip: conflict-free 16-byte
-                    // stores (lane stride 12 words), then three contiguous 512-byte warp stores
+                    // The warp's row segment (32 lanes x 48 B = 1536 contiguous bytes) goes through a
+                    // private shared-memory strip (conflict-free 16-byte stores at a 12-word lane
+                    // stride) and leaves as ONE bulk async copy issued by lane 0 (TMA engine,
+                    // cp.async.bulk shared -> global): fully coalesced HBM writes with no LDS / STG
+                    // wavefronts on the warp's LSU pipe.  Two strips alternate (one per row).
+                    float* strip = stage + half * 384;
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // strip's previous copy has read it
+                    __syncwarp();
                     if (active) {
-                        float4* sp = reinterpret_cast<float4*>(stage + 12 * lane);
+                        float4* sp = reinterpret_cast<float4*>(strip + 12 * lane);
                         sp[0] = make_float4(o[0], o[1], o[2], o[3]);
                         sp[1] = make_float4(o[4], o[5], o[6], o[7]);
                         sp[2] = make_float4(o[8], o[9], o[10], o[11]);
                     }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy
                     __syncwarp();
-                    float* wout = a.out_f32 + grow + (size_t)warp_X0 * 3;
-                    const int nvalid = min(32, (x1 - warp_X0) >> 2) * 3;      // valid 16-byte chunks of this warp's segment
-#pragma unroll
-                    for (int s = 0; s < 3; ++s) {
-                        const int c = s * 32 + lane;
-                        if (c < nvalid) *reinterpret_cast<float4*>(wout + 4 * c) = *reinterpret_cast<const float4*>(stage + 4 * c);
+                    if (lane == 0) {
+                        const int nbytes = min(32, (x1 - warp_X0) >> 2) * 48;
+                        float* wout = a.out_f32 + grow + (size_t)warp_X0 * 3;
+                        const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(strip);
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                     :: "l"(wout), "r"(saddr), "r"(nbytes) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
-                    __syncwarp();
                 } else if (active) {
 #pragma unroll
                     for (int k = 0; k < 12; ++k)
@@ -291,6 +298,7 @@ struct Tile {
         if (warp_X0 >= x1) return;                   // whole warp right of the image
         const bool active = X < x1;
         for (int m = (y0 >> 1) + threadIdx.y; 2 * m < y1; m += blockDim.y) item<ROI, VEC>(X, m, active, warp_X0);
+        if (VEC && F32OUT && (threadIdx.x & 31) == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
 };
 
@@ -374,7 +382,7 @@ __global__ void __launch_bounds__(MAXT, 3) collapse_kernel(const ColArgs a) {
     tl.t = t; tl.x0 = x0; tl.x1 = x1; tl.y0 = y0; tl.y1 = y1;
     tl.l1 = smf + g1.off - g1.r0 * g1.rs - g1.c0;
     tl.l1_rs = g1.rs; tl.l1_ps = g1.ps;
-    tl.stage = smf + a.stage_off + (tid >> 5) * 384;
+    tl.stage = smf + a.stage_off + (tid >> 5) * 768;
     bool any_hit = false;
     if (KMAX > 0) {
 #pragma unroll
@@ -474,8 +482,8 @@ extern "C" int vhr_collapse_addback_roi(vhr_ctx* ctx, const float* d_level, cons
     a.T = T; a.H = H; a.W = W; a.L = levels;
     PyrDims d = vhr_make_dims(W, H, levels);
     for (int l = 0; l <= VHR_MAX_LEVELS; ++l) { a.w[l] = d.w[l]; a.h[l] = d.h[l]; }
-    // tile: 256 x 32 by default (three CTAs per SM); tunable for experiments
-    int TW = 256, TH = 32;
+    // tile: 128 x 64 by default (best of the measured sweep, profiles/); tunable for experiments
+    int TW = 128, TH = 64;
     if (const char* e = getenv("VHR_COLLAPSE_TW")) TW = atoi(e);
     if (const char* e = getenv("VHR_COLLAPSE_TH")) TH = atoi(e);
     if (TW < 128 || TW % 128 != 0 || TW > 1024 || TH < 2 || TH % 2 != 0 || TH > 128) {
@@ -512,7 +520,7 @@ extern "C" int vhr_collapse_addback_roi(vhr_ctx* ctx, const float* d_level, cons
     // and the next level is only written by pass B (a barrier later), so every level lives at
     // offset 0; the store-transpose strips are only used after the last H is dead.
     const size_t szR = szX > szY ? szX : szY;
-    const size_t szS = (size_t)((cg * rg + 31) / 32) * 384;
+    const size_t szS = (size_t)((cg * rg + 31) / 32) * 768;
     a.bufX_off = 0;
     a.bufY_off = 0;
     a.bufH_off = (int)((szR + 3) & ~(size_t)3);
