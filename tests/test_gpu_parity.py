@@ -52,7 +52,7 @@ def test_synth_bit_identical(vhr, eng, shape):
 
 
 # ---------------------------------------------------------------------------------- pyramid
-@pytest.mark.parametrize("hw", [(144, 256), (480, 640), (135, 248), (97, 131), (61, 67), (9, 16), (5, 7)])
+@pytest.mark.parametrize("hw", [(144, 256), (480, 640), (90, 160), (67, 1920), (135, 248), (97, 131), (61, 67), (9, 16), (5, 7)])
 @pytest.mark.parametrize("levels", [1, 2, 3, 4])
 def test_pyrdown_cascade(vhr, eng, hw, levels):
     import torch
@@ -68,6 +68,20 @@ def test_pyrdown_cascade(vhr, eng, hw, levels):
         assert rel_err(got, ref) <= REL
 
 
+def test_pyrdown_generic_kernel_on_aligned_shapes(vhr, eng, monkeypatch):
+    """The generic kernel (used for W % 16 != 0) gives the same bits as the fast path."""
+    import torch
+    monkeypatch.setenv("VHR_PYRDOWN_GENERIC", "1")
+    rng = np.random.default_rng(77)
+    fr = rng.integers(0, 256, (2, 144, 256, 3), dtype=np.uint8)
+    frd = torch.as_tensor(fr, device=eng.tdev)
+    gen = eng.pyrdown(frd, 4).cpu().numpy()
+    monkeypatch.delenv("VHR_PYRDOWN_GENERIC")
+    fast = eng.pyrdown(frd, 4).cpu().numpy()
+    assert rel_err(gen, oevm.pyrdown_cascade(fr, 4)) <= REL
+    assert rel_err(fast, gen) <= 1e-6
+
+
 def test_pyrdown_many_frames_persistent_split(vhr, eng):
     """More frames than CTAs can take whole: shares start and end mid-frame."""
     import torch
@@ -75,6 +89,9 @@ def test_pyrdown_many_frames_persistent_split(vhr, eng):
     fr = rng.integers(0, 256, (700, 40, 64, 3), dtype=np.uint8)
     got = eng.pyrdown(torch.as_tensor(fr, device=eng.tdev), 2).cpu().numpy()
     np.testing.assert_array_equal(got, oevm.pyrdown_cascade(fr, 2).astype(np.float32))
+    fr = rng.integers(0, 256, (400, 70, 96, 3), dtype=np.uint8)          # odd level heights, 4 levels
+    got = eng.pyrdown(torch.as_tensor(fr, device=eng.tdev), 4).cpu().numpy()
+    assert rel_err(got, oevm.pyrdown_cascade(fr, 4)) <= REL
 
 
 # --------------------------------------------------------------------------------- bandpass

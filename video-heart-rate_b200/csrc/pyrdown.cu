@@ -21,6 +21,11 @@
 //   * Exactness: levels 1 and 2 are exact integers scaled by 2^-8 / 2^-16, hence bit-exact
 //     with cv2 / the float64 oracle; levels >= 3 round in float32 (tests: <= 1e-4 rel).
 #include "common.cuh"
+#include <stdlib.h>
+
+// fast path for W % 16 == 0 (pyrdown_fast.cu); VHR_ERR_UNSUPPORTED when the shape is not eligible
+int vhr_pyrdown_fast(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int W, int levels, float* d_level,
+                     cudaStream_t stream);
 
 namespace {
 
@@ -336,6 +341,13 @@ extern "C" int vhr_pyrdown_cascade(vhr_ctx* ctx, const uint8_t* d_frames, int T,
     VHR_REQUIRE(ctx, T >= 1 && H >= 1 && W >= 1, "bad shape");
     VHR_REQUIRE(ctx, levels >= 1 && levels <= VHR_MAX_LEVELS, "levels must be 1..6");
     VHR_REQUIRE(ctx, W <= 8192, "W > 8192 unsupported");
+    {
+        const char* force = getenv("VHR_PYRDOWN_GENERIC");      // test hook: exercise the generic kernel on any shape
+        if (!(force && force[0] == '1')) {
+            const int rc = vhr_pyrdown_fast(ctx, d_frames, T, H, W, levels, d_level, (cudaStream_t)stream);
+            if (rc != VHR_ERR_UNSUPPORTED) return rc;
+        }
+    }
     PyrArgs a;
     memset(&a, 0, sizeof(a));
     a.frames = d_frames;
