@@ -74,22 +74,26 @@ struct HPassF<3> {
     __device__ static __forceinline__ void run(const uint32_t (&)[9], uint32_t (&)[6]) {}
 };
 
+// Issue the loads of 9 words = bytes [24i-8, 24i+28) of the row at byte offset rowofs.  Nothing
+// here reads a loaded value: the frame-edge words are patched by fix_row_edges() right before
+// the row is consumed, so the loads stay in flight across a whole iteration (a predicated-off
+// instruction that names a pending register still waits on the scoreboard).
 __device__ __forceinline__ void load_row_fast(const uint8_t* __restrict__ tp, unsigned rowofs, int i, int nt1,
                                               uint32_t (&wd)[9]) {
-    // tp = frame + 24 i ; 9 words = bytes [24i-8, 24i+28) of the row at byte offset rowofs
-    const uint2* p = reinterpret_cast<const uint2*>(tp + rowofs);
+    const uint2* p = reinterpret_cast<const uint2*>(tp + rowofs);     // tp = frame + 24 i
     const uint2 o0 = __ldg(p), o1 = __ldg(p + 1), o2 = __ldg(p + 2);
     wd[2] = o0.x; wd[3] = o0.y; wd[4] = o1.x; wd[5] = o1.y; wd[6] = o2.x; wd[7] = o2.y;
-    if (i > 0) {
-        const uint2 l = __ldg(p - 1);
-        wd[0] = l.x; wd[1] = l.y;
-    } else {
+    const uint2 l = __ldg(p - (i > 0 ? 1 : 0));                        // thread 0: harmless in-bounds reload, patched later
+    wd[0] = l.x; wd[1] = l.y;
+    wd[8] = __ldg(reinterpret_cast<const uint32_t*>(tp + rowofs + (i < nt1 - 1 ? 24 : 20)));
+}
+__device__ __forceinline__ void fix_row_edges(int i, int nt1, uint32_t (&wd)[9]) {
+    if (i == 0) {
         wd[0] = __byte_perm(wd[3], 0, 0x3244);                 // pixels -2,-1 reflect to 2,1
         const uint32_t tt = __byte_perm(wd[2], wd[3], 0x5430);
         wd[1] = __byte_perm(tt, wd[4], 0x3214);
     }
-    if (i < nt1 - 1) wd[8] = __ldg(reinterpret_cast<const uint32_t*>(tp + rowofs + 24));
-    else wd[8] = __byte_perm(wd[6], wd[7], 0x0432);            // pixel W reflects to W-2
+    if (i == nt1 - 1) wd[8] = __byte_perm(wd[6], wd[7], 0x0432);   // pixel W reflects to W-2
 }
 
 template <int L>
@@ -102,18 +106,24 @@ struct FastStream {
     int lastr[VHR_MAX_LEVELS + 1];   // last row this segment needs per level
     uint32_t win[5][6];
     uint32_t pre[2][9];
+    // per-thread byte offsets into shared memory, computed once (the row / channel parts of
+    // every address are block-uniform and added from uniform registers)
+    int tapofs[VHR_MAX_LEVELS + 1][5];   // levels >= 3: byte offsets of the 5 horizontal taps in a ring row of level l-1
+    int hps[VHR_MAX_LEVELS + 1];         // plane stride (bytes) of the private H ring of level l
+    int rps[VHR_MAX_LEVELS + 1];         // plane stride (bytes) of the shared row ring of level l
 
-    __device__ FastStream(const FastArgs& a_, unsigned char* s) : a(a_), smem(s) {}
-
-    __device__ __forceinline__ uint16_t* ring1(int row, int ch) const {
-        return reinterpret_cast<uint16_t*>(smem + a.ring_off[1]) + ((row & 1) * 3 + ch) * a.ring_stride[1];
-    }
-    __device__ __forceinline__ float* ringf(int l, int row, int ch) const {
-        return reinterpret_cast<float*>(smem + a.ring_off[l]) + ((row & 1) * 3 + ch) * a.ring_stride[l];
-    }
-    template <typename Tv>
-    __device__ __forceinline__ Tv* hring(int l, int row, int ch) const {
-        return reinterpret_cast<Tv*>(smem + a.hring_off[l]) + ((row % HR) * 3 + ch) * a.w[l];
+    __device__ FastStream(const FastArgs& a_, unsigned char* s) : a(a_), smem(s) {
+        const int i = threadIdx.x;
+#pragma unroll
+        for (int l = 1; l <= L; ++l) {
+            hps[l] = a.w[l] * 4;
+            rps[l] = a.ring_stride[l] * (l == 1 ? 2 : 4);
+            if (l >= 3) {
+                const int wp = a.w[l - 1];
+#pragma unroll
+                for (int d = 0; d < 5; ++d) tapofs[l][d] = 4 * vhr_reflect101(2 * min(i, a.w[l] - 1) - 2 + d, wp);
+            }
+        }
     }
 
     __device__ __forceinline__ void begin_segment(int t, int r0, int r1) {
@@ -136,32 +146,38 @@ struct FastStream {
     template <int l>
     __device__ __forceinline__ void on_row(int r) {
         const int i = threadIdx.x;
+        const bool own = i < a.nt[l];
+        // block-uniform pieces of the addresses
+        unsigned char* const hbase = smem + a.hring_off[l] + (r % HR) * 3 * hps[l];        // H-ring slot of source row r
+        const unsigned char* const rsrc = smem + a.ring_off[l - 1] + (r & 1) * 3 * rps[l - 1];
         // horizontal pass of this thread's columns
-        if (i < a.nt[l]) {
+        if (own) {
             if constexpr (l == 2) {
                 // 2 px x 3 ch from planar uint16 pairs (apron of 4 entries on the left)
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {
-                    const uint16_t* p = ring1(r, ch) + 4 * i + 2;              // px 4i-2
+                    const unsigned char* p = rsrc + ch * rps[1] + 8 * i + 4;                 // px 4i-2
                     const uint32_t w0 = *reinterpret_cast<const uint32_t*>(p);
-                    const uint2 w12 = *reinterpret_cast<const uint2*>(p + 2);  // px 4i .. 4i+3
-                    const uint32_t w3 = *reinterpret_cast<const uint32_t*>(p + 6);
+                    const uint2 w12 = *reinterpret_cast<const uint2*>(p + 4);               // px 4i .. 4i+3
+                    const uint32_t w3 = *reinterpret_cast<const uint32_t*>(p + 12);
                     uint32_t o0 = __dp2a_lo(w0, 0x0401u, 0u);
                     o0 = __dp2a_lo(w12.x, 0x0406u, o0);
                     o0 = __dp2a_lo(w12.y, 0x0001u, o0);
                     uint32_t o1 = __dp2a_lo(w12.x, 0x0401u, 0u);
                     o1 = __dp2a_lo(w12.y, 0x0406u, o1);
                     o1 = __dp2a_lo(w3, 0x0001u, o1);
-                    *reinterpret_cast<uint2*>(hring<uint32_t>(2, r, ch) + 2 * i) = make_uint2(o0, o1);
+                    *reinterpret_cast<uint2*>(hbase + ch * hps[2] + 8 * i) = make_uint2(o0, o1);
                 }
             } else {
-                const int wp = a.w[l - 1];
-                const int x0 = vhr_reflect101(2 * i - 2, wp), x1 = vhr_reflect101(2 * i - 1, wp), x2 = 2 * i;
-                const int x3 = vhr_reflect101(2 * i + 1, wp), x4 = vhr_reflect101(2 * i + 2, wp);
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {
-                    const float* p = ringf(l - 1, r, ch);
-                    hring<float>(l, r, ch)[i] = p[x2] * 6.0f + (p[x1] + p[x3]) * 4.0f + p[x0] + p[x4];
+                    const unsigned char* p = rsrc + ch * rps[l - 1];
+                    const float t0 = *reinterpret_cast<const float*>(p + tapofs[l][0]);
+                    const float t1 = *reinterpret_cast<const float*>(p + tapofs[l][1]);
+                    const float t2 = *reinterpret_cast<const float*>(p + tapofs[l][2]);
+                    const float t3 = *reinterpret_cast<const float*>(p + tapofs[l][3]);
+                    const float t4 = *reinterpret_cast<const float*>(p + tapofs[l][4]);
+                    *reinterpret_cast<float*>(hbase + ch * hps[l] + 4 * i) = t2 * 6.0f + (t1 + t3) * 4.0f + t0 + t4;
                 }
             }
         }
@@ -169,18 +185,30 @@ struct FastStream {
         const int hp = a.h[l - 1];
         while (nextr[l] <= lastr[l] && min(2 * nextr[l] + 2, hp - 1) <= r) {
             const int q = nextr[l];
-            int rr[5];
+            // slot byte offsets of the five source rows (block-uniform; reflected at the frame's
+            // top / bottom only)
+            int so[5];
+            const int ss = 3 * hps[l];
+            if (2 * q - 2 >= 0 && 2 * q + 2 <= hp - 1) {        // interior: five consecutive rows, newest = 2q+2
+                int sl = (2 * q - 2) % HR;
 #pragma unroll
-            for (int d = 0; d < 5; ++d) rr[d] = vhr_reflect101(2 * q - 2 + d, hp);
-            if (i < a.nt[l]) {
+                for (int d = 0; d < 5; ++d) { so[d] = sl * ss; sl = (sl == HR - 1) ? 0 : sl + 1; }
+            } else {
+#pragma unroll
+                for (int d = 0; d < 5; ++d) so[d] = (vhr_reflect101(2 * q - 2 + d, hp) % HR) * ss;
+            }
+            const unsigned char* const hb = smem + a.hring_off[l];
+            if (own) {
                 if constexpr (l == 2) {
+                    unsigned char* const dst = smem + a.ring_off[2] + (q & 1) * 3 * rps[2];
 #pragma unroll
                     for (int ch = 0; ch < 3; ++ch) {
-                        const uint2 va = *reinterpret_cast<const uint2*>(hring<uint32_t>(2, rr[0], ch) + 2 * i);
-                        const uint2 vb = *reinterpret_cast<const uint2*>(hring<uint32_t>(2, rr[1], ch) + 2 * i);
-                        const uint2 vc = *reinterpret_cast<const uint2*>(hring<uint32_t>(2, rr[2], ch) + 2 * i);
-                        const uint2 vd = *reinterpret_cast<const uint2*>(hring<uint32_t>(2, rr[3], ch) + 2 * i);
-                        const uint2 ve = *reinterpret_cast<const uint2*>(hring<uint32_t>(2, rr[4], ch) + 2 * i);
+                        const unsigned char* hc = hb + ch * hps[2] + 8 * i;
+                        const uint2 va = *reinterpret_cast<const uint2*>(hc + so[0]);
+                        const uint2 vb = *reinterpret_cast<const uint2*>(hc + so[1]);
+                        const uint2 vc = *reinterpret_cast<const uint2*>(hc + so[2]);
+                        const uint2 vd = *reinterpret_cast<const uint2*>(hc + so[3]);
+                        const uint2 ve = *reinterpret_cast<const uint2*>(hc + so[4]);
                         const uint32_t s0 = (va.x + ve.x) + 4u * (vb.x + vd.x) + 6u * vc.x;     // < 2^24: exact
                         const uint32_t s1 = (va.y + ve.y) + 4u * (vb.y + vd.y) + 6u * vc.y;
                         const float f0 = (float)s0 * (1.0f / 65536.0f), f1 = (float)s1 * (1.0f / 65536.0f);
@@ -188,18 +216,20 @@ struct FastStream {
                             float* o = out_frame + ((size_t)q * a.w[2] + 2 * i) * 3 + ch;
                             o[0] = f0; o[3] = f1;
                         } else {
-                            *reinterpret_cast<float2*>(ringf(2, q, ch) + 2 * i) = make_float2(f0, f1);
+                            *reinterpret_cast<float2*>(dst + ch * rps[2] + 8 * i) = make_float2(f0, f1);
                         }
                     }
                 } else {
+                    unsigned char* const dst = smem + a.ring_off[l < L ? l : 1] + (q & 1) * 3 * rps[l];
 #pragma unroll
                     for (int ch = 0; ch < 3; ++ch) {
-                        const float s = hring<float>(l, rr[2], ch)[i] * 6.0f +
-                                        (hring<float>(l, rr[1], ch)[i] + hring<float>(l, rr[3], ch)[i]) * 4.0f +
-                                        hring<float>(l, rr[0], ch)[i] + hring<float>(l, rr[4], ch)[i];
+                        const unsigned char* hc = hb + ch * hps[l] + 4 * i;
+                        const float s = *reinterpret_cast<const float*>(hc + so[2]) * 6.0f +
+                                        (*reinterpret_cast<const float*>(hc + so[1]) + *reinterpret_cast<const float*>(hc + so[3])) * 4.0f +
+                                        *reinterpret_cast<const float*>(hc + so[0]) + *reinterpret_cast<const float*>(hc + so[4]);
                         const float v = s * (1.0f / 256.0f);
                         if constexpr (l == L) out_frame[((size_t)q * a.w[l] + i) * 3 + ch] = v;
-                        else ringf(l, q, ch)[i] = v;
+                        else *reinterpret_cast<float*>(dst + ch * rps[l] + 4 * i) = v;
                     }
                 }
             }
@@ -221,6 +251,7 @@ struct FastStream {
             for (int d = 0; d < 5; ++d) {
                 uint32_t wd[9];
                 load_row_fast(tp, rowofs(2 * first - 2 + d), i, a.nt[1], wd);
+                fix_row_edges(i, a.nt[1], wd);
                 HPassF<0>::run(wd, win[d]);
             }
         }
@@ -230,6 +261,8 @@ struct FastStream {
                 if (r != first) {
 #pragma unroll
                     for (int k = 0; k < 6; ++k) { win[0][k] = win[2][k]; win[1][k] = win[3][k]; win[2][k] = win[4][k]; }
+                    fix_row_edges(i, a.nt[1], pre[0]);
+                    fix_row_edges(i, a.nt[1], pre[1]);
                     HPassF<0>::run(pre[0], win[3]);
                     HPassF<0>::run(pre[1], win[4]);
                 }
@@ -250,13 +283,14 @@ struct FastStream {
                         o[9 + ch] = (float)(v[2 * ch + 1] >> 16) * (1.0f / 256.0f);
                     }
                 } else {
+                    unsigned char* const dst = smem + a.ring_off[1] + (r & 1) * 3 * rps[1] + 8 * i;
 #pragma unroll
                     for (int ch = 0; ch < 3; ++ch) {
-                        uint16_t* p = ring1(r, ch);
-                        *reinterpret_cast<uint2*>(p + 4 * i + 4) = make_uint2(v[2 * ch], v[2 * ch + 1]);
+                        unsigned char* p = dst + ch * rps[1];
+                        *reinterpret_cast<uint2*>(p + 8) = make_uint2(v[2 * ch], v[2 * ch + 1]);        // px 4i .. 4i+3 (apron of 4)
                         // reflect-101 aprons: px -2,-1 <- px 2,1 ; px w1, w1+1 <- px w1-2, w1-3
-                        if (i == 0) *reinterpret_cast<uint32_t*>(p + 2) = __byte_perm(v[2 * ch + 1], v[2 * ch], 0x7610);
-                        if (i == a.nt[1] - 1) *reinterpret_cast<uint32_t*>(p + 4 * i + 8) = __byte_perm(v[2 * ch + 1], v[2 * ch], 0x7610);
+                        if (i == 0) *reinterpret_cast<uint32_t*>(p + 4) = __byte_perm(v[2 * ch + 1], v[2 * ch], 0x7610);
+                        if (i == a.nt[1] - 1) *reinterpret_cast<uint32_t*>(p + 16) = __byte_perm(v[2 * ch + 1], v[2 * ch], 0x7610);
                     }
                 }
             }
