@@ -74,6 +74,7 @@ int vhr_destroy(vhr_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->tw) cudaFree(ctx->tw);
+    if (ctx->mask) cudaFree(ctx->mask);
     if (ctx->hostpath) cudaFree(ctx->hostpath);
     delete ctx;
     return VHR_OK;

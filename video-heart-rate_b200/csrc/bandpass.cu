@@ -4,7 +4,16 @@
 // y = irfft(mask * rfft(x), n=T) with mask = (f_lo <= rfftfreq(T,1/fps) <= f_hi), DC dropped
 // (inclusive edges like rppg_VIDEO.py:140,196).
 //
-// Form used here: band-limited DFT pair.  Only the B kept bins are ever needed
+// Two forms, same result:
+//  (1) T = 2^a 3^b 5^c (1800, 300, 150 ...): in-place mixed-radix FFT in shared memory, two real
+//      series packed into one complex transform: decimation-in-frequency forward (natural ->
+//      digit-reversed), multiply by a host-built mask laid out in digit-reversed order (kept
+//      bins k and T-k, gain/T folded in), decimation-in-time inverse (digit-reversed -> natural).
+//      No reordering pass, one buffer, radix-5/3/4/2 butterflies; ~20x fewer instructions than
+//      form (2) at T = 1800.
+//  (2) any other T: band-limited DFT pair (below).
+//
+// Form (2): band-limited DFT pair.  Only the B kept bins are ever needed
 // (B = 199 of 901 at T = 1800), so each CTA takes PX pixel series (T x PX floats in shared
 // memory), computes X_k = sum_t x_t e^{-2 pi i k t / T} for the kept k only, then
 // y_t = (g / T) sum_k w_k Re(X_k e^{+2 pi i k t / T}), w_k = 2 (1 for the Nyquist bin).
@@ -15,6 +24,7 @@
 #include "common.cuh"
 #include <math.h>
 #include <vector>
+#include <stdlib.h>
 
 namespace {
 
@@ -122,6 +132,163 @@ __global__ void zero_fill_kernel(float* out, long long n) {
     for (; i < n; i += stride) out[i] = 0.f;
 }
 
+
+// ---------------------------------------------------------------------------------- form (1)
+constexpr int FG = 4;            // complex series per CTA (= 8 pixel series, one 32-byte sector per time step)
+constexpr int FT = 256;
+constexpr int MAXPASS = 16;
+
+struct FftArgs {
+    const float* in;
+    float* out;
+    const float2* tw;        // T entries (cos, sin)(2 pi m / T)
+    const float* mask;       // T entries, digit-reversed order: gain/T on kept bins, else 0
+    int T;
+    long long P;
+    int npass;
+    int radix[MAXPASS];
+    int sub[MAXPASS];        // sub-transform length n at this pass (n_0 = T)
+    unsigned inv_m[MAXPASS]; // magic reciprocal of m = n / r
+    int pair_ok;             // P even: float2 global accesses allowed
+};
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// multiply by -i (forward) or +i (inverse)
+template <bool INV>
+__device__ __forceinline__ float2 mul_mi(float2 a) { return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x); }
+
+template <int R, bool INV>
+__device__ __forceinline__ void dft_small(float2 (&v)[R]) {
+    if constexpr (R == 2) {
+        const float2 a = v[0], b = v[1];
+        v[0] = cadd(a, b); v[1] = csub(a, b);
+    } else if constexpr (R == 3) {
+        const float2 t1 = cadd(v[1], v[2]);
+        const float2 t2 = make_float2(v[0].x - 0.5f * t1.x, v[0].y - 0.5f * t1.y);
+        const float2 d = csub(v[1], v[2]);
+        const float2 t3 = mul_mi<INV>(make_float2(0.8660254037844386f * d.x, 0.8660254037844386f * d.y));
+        v[0] = cadd(v[0], t1); v[1] = cadd(t2, t3); v[2] = csub(t2, t3);
+    } else if constexpr (R == 4) {
+        const float2 t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]), t2 = cadd(v[1], v[3]);
+        const float2 t3 = mul_mi<INV>(csub(v[1], v[3]));
+        v[0] = cadd(t0, t2); v[2] = csub(t0, t2); v[1] = cadd(t1, t3); v[3] = csub(t1, t3);
+    } else {
+        static_assert(R == 5, "radix");
+        const float c1 = 0.30901699437494745f, c2 = -0.8090169943749475f, s1 = 0.9510565162951535f, s2 = 0.5877852522924731f;
+        const float2 t1 = cadd(v[1], v[4]), t2 = cadd(v[2], v[3]), t3 = csub(v[1], v[4]), t4 = csub(v[2], v[3]);
+        const float2 m1 = make_float2(v[0].x + c1 * t1.x + c2 * t2.x, v[0].y + c1 * t1.y + c2 * t2.y);
+        const float2 m2 = make_float2(v[0].x + c2 * t1.x + c1 * t2.x, v[0].y + c2 * t1.y + c1 * t2.y);
+        const float2 n1 = mul_mi<INV>(make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y));
+        const float2 n2 = mul_mi<INV>(make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y));
+        v[0] = make_float2(v[0].x + t1.x + t2.x, v[0].y + t1.y + t2.y);
+        v[1] = cadd(m1, n1); v[4] = csub(m1, n1); v[2] = cadd(m2, n2); v[3] = csub(m2, n2);
+    }
+}
+
+// one radix-R pass over all FG series held in z[FG][T]; DIF (forward) twiddles after the
+// butterfly, DIT (inverse) conjugate twiddles before it
+template <int R, bool INV>
+__device__ __forceinline__ void fft_pass(float2* __restrict__ z, const float2* __restrict__ tws, int T, int n,
+                                         unsigned inv_m) {
+    const int m = n / R, step = T / n, nb = T / R;
+    for (int b = threadIdx.x; b < nb; b += FT) {
+        const int block = inv_m ? (int)__umulhi((unsigned)b, inv_m) : b;     // inv_m == 0 encodes m == 1
+        const int j = b - block * m;
+        const int base = block * n + j;
+        float2 w[R];
+#pragma unroll
+        for (int q = 1; q < R; ++q) {
+            const float2 t = tws[j * q * step];
+            w[q] = make_float2(t.x, INV ? t.y : -t.y);
+        }
+#pragma unroll
+        for (int s = 0; s < FG; ++s) {
+            float2* zs = z + (size_t)s * T + base;
+            float2 v[R];
+#pragma unroll
+            for (int q = 0; q < R; ++q) v[q] = zs[q * m];
+            if (INV) {
+#pragma unroll
+                for (int q = 1; q < R; ++q) v[q] = cmul(v[q], w[q]);
+            }
+            dft_small<R, INV>(v);
+            if (!INV) {
+#pragma unroll
+                for (int q = 1; q < R; ++q) v[q] = cmul(v[q], w[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < R; ++q) zs[q * m] = v[q];
+        }
+    }
+}
+
+template <bool INV>
+__device__ __forceinline__ void fft_dispatch(float2* z, const float2* tws, int T, int r, int n, unsigned inv_m) {
+    switch (r) {
+        case 5: fft_pass<5, INV>(z, tws, T, n, inv_m); break;
+        case 3: fft_pass<3, INV>(z, tws, T, n, inv_m); break;
+        case 4: fft_pass<4, INV>(z, tws, T, n, inv_m); break;
+        default: fft_pass<2, INV>(z, tws, T, n, inv_m); break;
+    }
+}
+
+__global__ void __launch_bounds__(FT) bandpass_fft_kernel(const __grid_constant__ FftArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* z = reinterpret_cast<float2*>(smem_raw);                  // [FG][T]
+    float2* tws = z + (size_t)FG * a.T;                               // [T]
+    const int T = a.T;
+    const long long p0 = (long long)blockIdx.x * (2 * FG);
+    for (int m = threadIdx.x; m < T; m += FT) tws[m] = a.tw[m];
+    // tile load: (px 2s, px 2s+1) of time step t -> z[s][t]; the series' first sample is
+    // subtracted (a constant only feeds the dropped DC bin; keeps float32 error at signal scale)
+    {
+        const int s = threadIdx.x % FG;                 // FT % FG == 0: fixed series per thread
+        const long long pa = p0 + 2 * s;
+        const bool va = pa < a.P, vb = pa + 1 < a.P;
+        float2 x0 = make_float2(0.f, 0.f);
+        if (va) x0.x = __ldg(a.in + pa);
+        if (vb) x0.y = __ldg(a.in + pa + 1);
+        for (int idx = threadIdx.x; idx < T * FG; idx += FT) {
+            const int t = idx / FG;
+            float2 v = make_float2(0.f, 0.f);
+            const float* src = a.in + (size_t)t * a.P + pa;
+            if (a.pair_ok && vb) v = __ldg(reinterpret_cast<const float2*>(src));
+            else { if (va) v.x = __ldg(src); if (vb) v.y = __ldg(src + 1); }
+            z[(size_t)s * T + t] = make_float2(v.x - x0.x, v.y - x0.y);
+        }
+    }
+    __syncthreads();
+    for (int ps = 0; ps < a.npass; ++ps) {
+        fft_dispatch<false>(z, tws, T, a.radix[ps], a.sub[ps], a.inv_m[ps]);
+        __syncthreads();
+    }
+    for (int idx = threadIdx.x; idx < T * FG; idx += FT) {
+        const int s = idx / T, pos = idx - s * T;
+        const float mk = __ldg(a.mask + pos);
+        float2 v = z[idx];
+        z[idx] = make_float2(v.x * mk, v.y * mk);
+    }
+    __syncthreads();
+    for (int ps = a.npass - 1; ps >= 0; --ps) {
+        fft_dispatch<true>(z, tws, T, a.radix[ps], a.sub[ps], a.inv_m[ps]);
+        __syncthreads();
+    }
+    {
+        const int s = threadIdx.x % FG;
+        const long long pa = p0 + 2 * s;
+        const bool va = pa < a.P, vb = pa + 1 < a.P;
+        for (int idx = threadIdx.x; idx < T * FG; idx += FT) {
+            const int t = idx / FG;
+            const float2 v = z[(size_t)s * T + t];
+            float* dst = a.out + (size_t)t * a.P + pa;
+            if (a.pair_ok && vb) *reinterpret_cast<float2*>(dst) = v;
+            else { if (va) dst[0] = v.x; if (vb) dst[1] = v.y; }
+        }
+    }
+}
+
 }  // namespace
 
 static int ensure_twiddles(vhr_ctx* ctx, int T, cudaStream_t stream) {
@@ -159,6 +326,57 @@ extern "C" int vhr_temporal_bandpass(vhr_ctx* ctx, const float* d_in, float* d_o
     }
     int rc = ensure_twiddles(ctx, T, stream);
     if (rc != VHR_OK) return rc;
+    {   // form (1): mixed-radix FFT when T factors into 2, 3, 5 and the tile fits in shared memory
+        const char* force = getenv("VHR_BANDPASS_DFT");          // test hook: exercise form (2)
+        std::vector<int> radices;
+        int n = T;
+        for (int f : {5, 3}) while (n % f == 0) { radices.push_back(f); n /= f; }
+        while (n % 4 == 0) { radices.push_back(4); n /= 4; }
+        while (n % 2 == 0) { radices.push_back(2); n /= 2; }
+        const size_t smem_fft = (size_t)T * 8 * (FG + 1);
+        if (n == 1 && T >= 2 && (int)radices.size() <= MAXPASS && (long long)smem_fft <= ctx->smem_optin && T <= 65535 &&
+            !(force && force[0] == '1')) {
+            FftArgs fa;
+            memset(&fa, 0, sizeof(fa));
+            fa.in = d_in; fa.out = d_out; fa.tw = ctx->tw; fa.T = T; fa.P = P;
+            fa.npass = (int)radices.size();
+            int sub = T;
+            for (int i = 0; i < fa.npass; ++i) {
+                fa.radix[i] = radices[i];
+                fa.sub[i] = sub;
+                const unsigned mm = (unsigned)(sub / radices[i]);
+                fa.inv_m[i] = mm > 1 ? 0xFFFFFFFFu / mm + 1u : 0u;       // exact for b < 65536
+                sub /= radices[i];
+            }
+            fa.pair_ok = (P % 2 == 0) && ((reinterpret_cast<uintptr_t>(d_in) & 7) == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 7) == 0);
+            // mask in digit-reversed (DIF output) order; cached per (T, band, gain)
+            if (!(ctx->mask && ctx->mask_T == T && ctx->mask_k0 == k0 && ctx->mask_k1 == k1 && ctx->mask_gain == gain)) {
+                std::vector<float> hm((size_t)T);
+                const float g = (float)((double)gain / (double)T);
+                for (int pos = 0; pos < T; ++pos) {
+                    int rem = pos, sb = T, k = 0, mul = 1;
+                    for (int r : radices) { sb /= r; const int q = rem / sb; rem -= q * sb; k += mul * q; mul *= r; }
+                    const int kk = k <= T - k ? k : T - k;          // bins k and T-k share |f|
+                    hm[pos] = (kk >= k0 && kk <= k1) ? g : 0.0f;
+                }
+                if (ctx->mask && ctx->mask_T != T) {
+                    VHR_CHECK_CUDA(ctx, cudaDeviceSynchronize());
+                    VHR_CHECK_CUDA(ctx, cudaFree(ctx->mask));
+                    ctx->mask = nullptr;
+                }
+                if (!ctx->mask) VHR_CHECK_CUDA(ctx, cudaMalloc(&ctx->mask, sizeof(float) * (size_t)T));
+                VHR_CHECK_CUDA(ctx, cudaStreamSynchronize(stream));      // previous users of the cached mask
+                VHR_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->mask, hm.data(), sizeof(float) * (size_t)T, cudaMemcpyHostToDevice, stream));
+                VHR_CHECK_CUDA(ctx, cudaStreamSynchronize(stream));
+                ctx->mask_T = T; ctx->mask_k0 = k0; ctx->mask_k1 = k1; ctx->mask_gain = gain;
+            }
+            fa.mask = ctx->mask;
+            VHR_CHECK_CUDA(ctx, cudaFuncSetAttribute(bandpass_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
+            const long long blocks = (P + 2 * FG - 1) / (2 * FG);
+            bandpass_fft_kernel<<<(unsigned)blocks, FT, smem_fft, stream>>>(fa);
+            return vhr_after_launch(ctx, "bandpass_fft_kernel");
+        }
+    }
     BpArgs a;
     a.in = d_in; a.out = d_out; a.tw = ctx->tw; a.T = T; a.P = P;
     a.k0 = k0; a.nb = nb;

@@ -68,9 +68,9 @@ __device__ __forceinline__ void expand_h(float* __restrict__ sm, const Geo S, co
                                          int g_lo, int g_hi, int tid, int nthreads) {
     const int ng = g_hi - g_lo + 1;
     const int n = (p_hi - p_lo + 1) * ng;
-    const unsigned inv = 0xFFFFFFFFu / (unsigned)ng + 1u;       // it / ng == umulhi(it, inv) for it < 65536
+    const unsigned inv = ng > 1 ? 0xFFFFFFFFu / (unsigned)ng + 1u : 0u;   // it / ng == umulhi(it, inv) for it < 65536; 0 encodes ng == 1
     for (int it = tid; it < n; it += nthreads) {
-        const int pr = (int)__umulhi((unsigned)it, inv);
+        const int pr = inv ? (int)__umulhi((unsigned)it, inv) : it;
         const int g = g_lo + (it - pr * ng), p = p_lo + pr;
         const int so = (p - S.r0) * S.rs + (2 * g - 1 - S.c0);
         const int ho = (p - Hh.r0) * Hh.rs + (4 * g - 1 - Hh.c0);
@@ -93,9 +93,9 @@ __device__ __forceinline__ void expand_v(float* __restrict__ sm, const Geo Hh, c
                                          int g_lo, int g_hi, int tid, int nthreads) {
     const int ng = g_hi - g_lo + 1;
     const int n = (p_hi - p_lo + 1) * ng;
-    const unsigned inv = 0xFFFFFFFFu / (unsigned)ng + 1u;
+    const unsigned inv = ng > 1 ? 0xFFFFFFFFu / (unsigned)ng + 1u : 0u;
     for (int it = tid; it < n; it += nthreads) {
-        const int pr = (int)__umulhi((unsigned)it, inv);
+        const int pr = inv ? (int)__umulhi((unsigned)it, inv) : it;
         const int g = g_lo + (it - pr * ng), p = p_lo + pr;
         const int ho = (p - Hh.r0) * Hh.rs + (4 * g - 1 - Hh.c0);
         const int dofs = (2 * p - D.r0) * D.rs + (4 * g - 1 - D.c0);

@@ -19,6 +19,10 @@ struct vhr_ctx {
     // cached twiddle table for the temporal bandpass
     float2* tw = nullptr;
     int tw_T = 0;
+    // cached digit-reversed band mask of the FFT bandpass
+    float* mask = nullptr;
+    int mask_T = 0, mask_k0 = -1, mask_k1 = -1;
+    float mask_gain = 0.f;
     // context-owned buffers of the *_host convenience path
     void* hostpath = nullptr;
     size_t hostpath_bytes = 0;
