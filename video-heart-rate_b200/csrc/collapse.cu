@@ -184,9 +184,9 @@ struct Tile {
                 const float2 c0 = *reinterpret_cast<const float2*>(pl + 2 * l1_rs), c1 = *reinterpret_cast<const float2*>(pl + 2 * l1_rs + 2);
                 const float av[4] = {a0.x, a0.y, a1.x, a1.y}, bv[4] = {b0.x, b0.y, b1.x, b1.y}, cv[4] = {c0.x, c0.y, c1.x, c1.y};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    ve[ch][j] = fmaf(av[j] + cv[j], 0.125f, bv[j] * 0.75f);
-                    vo[ch][j] = (bv[j] + cv[j]) * 0.5f;
+                for (int j = 0; j < 4; ++j) {      // UNSCALED (x8 / x2): the scaling is folded into the horizontal weights
+                    ve[ch][j] = fmaf(bv[j], 6.0f, av[j] + cv[j]);
+                    vo[ch][j] = bv[j] + cv[j];
                 }
             }
         }
@@ -219,11 +219,13 @@ struct Tile {
                     // uint8 -> float: 0x4B0000xx = 2^23 + xx
                     const float f = __uint_as_float(__byte_perm(ww[k >> 2], 0x4B000000u, 0x7440 + (k & 3))) - 8388608.0f;
                     const float (&v)[4] = half ? vo[ch] : ve[ch];
+                    // even row: v is x8 -> (v0+v2)/64 + 6 v1/64, (v1+v2)/16 ; odd row: v is x2 -> /16, 6/16, /4
+                    const float we = half ? 0.0625f : 0.015625f, wc = half ? 0.375f : 0.09375f, wo = half ? 0.25f : 0.0625f;
                     float up;
-                    if (px == 0) up = fmaf(v[0] + v[2], 0.125f, fmaf(v[1], 0.75f, f));
-                    else if (px == 1) up = fmaf(v[1] + v[2], 0.5f, f);
-                    else if (px == 2) up = fmaf(v[1] + v[3], 0.125f, fmaf(v[2], 0.75f, f));
-                    else up = fmaf(v[2] + v[3], 0.5f, f);
+                    if (px == 0) up = fmaf(v[0] + v[2], we, fmaf(v[1], wc, f));
+                    else if (px == 1) up = fmaf(v[1] + v[2], wo, f);
+                    else if (px == 2) up = fmaf(v[1] + v[3], we, fmaf(v[2], wc, f));
+                    else up = fmaf(v[2] + v[3], wo, f);
                     o[k] = up;
                 }
             }
