@@ -159,20 +159,24 @@ struct Tile {
 
     // one work item: pixels X..X+3, rows 2m and 2m+1.  `active` is false for lanes right of
     // the tile's valid width (they still take part in the warp-wide store transpose).
+    // issue the uint8 loads of rows 2m, 2m+1 for pixels X..X+3 (VEC path); nothing reads them here
+    __device__ __forceinline__ void load_pixels(int X, int m, bool active, uint32_t (&wq)[2][3]) const {
+        if (!active || 2 * m >= y1) return;
+        const size_t row_elems = (size_t)a.W * 3;
+        const size_t g0 = ((size_t)t * a.H + 2 * m) * row_elems + (size_t)X * 3;
+        const uint32_t* fp = reinterpret_cast<const uint32_t*>(a.frames + g0);
+        wq[0][0] = __ldg(fp); wq[0][1] = __ldg(fp + 1); wq[0][2] = __ldg(fp + 2);
+        if (2 * m + 1 < y1) {
+            const uint32_t* fq = reinterpret_cast<const uint32_t*>(a.frames + g0 + row_elems);
+            wq[1][0] = __ldg(fq); wq[1][1] = __ldg(fq + 1); wq[1][2] = __ldg(fq + 2);
+        }
+    }
+
     template <bool ROI, bool VEC>
-    __device__ __forceinline__ void item(int X, int m, bool active, int warp_X0) {
+    __device__ __forceinline__ void item(int X, int m, bool active, int warp_X0, const uint32_t (&wq)[2][3]) {
         float ve[3][4], vo[3][4];
         const size_t row_elems = (size_t)a.W * 3;
         const size_t g0 = ((size_t)t * a.H + 2 * m) * row_elems + (size_t)X * 3;
-        uint32_t wq[2][3];
-        if (VEC && active) {                          // both rows' pixels in flight before any shared-memory work
-            const uint32_t* fp = reinterpret_cast<const uint32_t*>(a.frames + g0);
-            wq[0][0] = __ldg(fp); wq[0][1] = __ldg(fp + 1); wq[0][2] = __ldg(fp + 2);
-            if (2 * m + 1 < y1) {
-                const uint32_t* fq = reinterpret_cast<const uint32_t*>(a.frames + g0 + row_elems);
-                wq[1][0] = __ldg(fq); wq[1][1] = __ldg(fq + 1); wq[1][2] = __ldg(fq + 2);
-            }
-        }
         if (active) {
             const int J = X >> 1;
             const float* pl0 = l1 + (m - 1) * l1_rs + (J - 1);
@@ -293,13 +297,27 @@ struct Tile {
         }
     }
 
+    // `wfirst`: pixels of this thread's first item, loaded before the tile prologue so their
+    // DRAM latency overlaps the region build; every later item's loads are issued one item ahead.
     template <bool ROI, bool VEC>
-    __device__ __forceinline__ void run() {
+    __device__ __forceinline__ void run(uint32_t (&wfirst)[2][3]) {
         const int X = x0 + 4 * threadIdx.x;
         const int warp_X0 = x0 + 4 * (threadIdx.x & ~31);
         if (warp_X0 >= x1) return;                   // whole warp right of the image
         const bool active = X < x1;
-        for (int m = (y0 >> 1) + threadIdx.y; 2 * m < y1; m += blockDim.y) item<ROI, VEC>(X, m, active, warp_X0);
+        uint32_t wcur[2][3], wnext[2][3];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { wcur[r][k] = wfirst[r][k]; wnext[r][k] = 0; }
+        for (int m = (y0 >> 1) + threadIdx.y; 2 * m < y1; m += blockDim.y) {
+            if (VEC) load_pixels(X, m + blockDim.y, active, wnext);
+            item<ROI, VEC>(X, m, active, warp_X0, wcur);
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) wcur[r][k] = wnext[r][k];
+        }
         if (VEC && F32OUT && (threadIdx.x & 31) == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
 };
@@ -319,11 +337,36 @@ __global__ void __launch_bounds__(MAXT, 3) collapse_kernel(const ColArgs a) {
     const int y0 = by * a.TH, y1 = min(a.H, y0 + a.TH);
     const int L = a.L;
 
+    // the first work item's pixels: in flight during the whole region build
+    Tile<KMAX, F32OUT, U8OUT> tl(a);
+    tl.t = t; tl.x0 = x0; tl.x1 = x1; tl.y0 = y0; tl.y1 = y1;
+    uint32_t wfirst[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    if (a.vec_ok) tl.load_pixels(x0 + 4 * (int)threadIdx.x, (y0 >> 1) + (int)threadIdx.y, x0 + 4 * (int)threadIdx.x < x1, wfirst);
+
     // regions [ra,rb] x [ca,cb] (inclusive, inside the image) needed at each level and their
     // storage geometry: computed once per tile by threads 1..L into shared memory (dynamically
-    // indexed per-thread arrays would live in local memory and be re-read in every loop)
+    // indexed per-thread arrays would live in local memory and be re-read in every loop).
+    // Every thread also derives the level-L geometry itself so the gather from HBM below is
+    // issued immediately, not behind the geometry barrier.
     __shared__ int s_reg[VHR_MAX_LEVELS + 1][4];       // ra, rb, ca, cb
     __shared__ Geo s_geo[VHR_MAX_LEVELS + 1];
+    Geo qL;
+    int raL, rbL, caL, cbL;
+    {
+        int ra = y0, rb = y1 - 1, ca = x0, cb = x1 - 1;
+        for (int l = 1; l <= L; ++l) {
+            ra = max(0, (ra >> 1) - 1);
+            rb = min(a.h[l] - 1, (rb >> 1) + 1);
+            ca = max(0, (ca >> 1) - 1);
+            cb = min(a.w[l] - 1, (cb >> 1) + 1);
+        }
+        raL = ra; rbL = rb; caL = ca; cbL = cb;
+        qL.c0 = 4 * (ca >> 2) - 5;
+        qL.r0 = ra - 2;
+        qL.rs = ((cb + 8 - qL.c0) + 3) & ~3;
+        qL.ps = (rb - ra + 5) * qL.rs;
+        qL.off = 0;
+    }
     if (tid >= 1 && tid <= L) {
         int ra = y0, rb = y1 - 1, ca = x0, cb = x1 - 1;
         for (int l = 1; l <= tid; ++l) {
@@ -341,12 +384,10 @@ __global__ void __launch_bounds__(MAXT, 3) collapse_kernel(const ColArgs a) {
         s_geo[tid] = q;
         s_reg[tid][0] = ra; s_reg[tid][1] = rb; s_reg[tid][2] = ca; s_reg[tid][3] = cb;
     }
-    __syncthreads();
 
     // ---- level L region (+ apron, border-mapped at load time) from HBM into planar smem ----
     {
-        const Geo q = s_geo[L];
-        const int raL = s_reg[L][0], rbL = s_reg[L][1], caL = s_reg[L][2], cbL = s_reg[L][3];
+        const Geo q = qL;
         const int nr = rbL - raL + 3, nc3 = (cbL - caL + 3) * 3;
         const unsigned inv = 0xFFFFFFFFu / (unsigned)nc3 + 1u;
         const float* src = a.lvl + ((size_t)t * a.h[L] * a.w[L]) * 3;
@@ -360,6 +401,7 @@ __global__ void __launch_bounds__(MAXT, 3) collapse_kernel(const ColArgs a) {
     }
     // ---- levels L-1 .. 1: separable expansion, aprons rewritten after each level ----------
     for (int l = L - 1; l >= 1; --l) {
+        __syncthreads();                              // level l+1 complete (and, first time round, the geometry written)
         const Geo S = s_geo[l + 1], D = s_geo[l];
         const int ral = s_reg[l][0], rbl = s_reg[l][1], cal = s_reg[l][2], cbl = s_reg[l][3];
         Geo hh;                                       // H rows: source row indexing, destination column indexing
@@ -369,7 +411,6 @@ __global__ void __launch_bounds__(MAXT, 3) collapse_kernel(const ColArgs a) {
         hh.off = a.bufH_off;
         const int g_lo = (cal + 1) >> 2, g_hi = (cbl + 1) >> 2;
         const int p_lo = ral >> 1, p_hi = rbl >> 1;
-        __syncthreads();
         expand_h(smf, S, hh, p_lo - 1, p_hi + 1, g_lo, g_hi, tid, nthreads);
         __syncthreads();
         expand_v(smf, hh, D, p_lo, p_hi, g_lo, g_hi, tid, nthreads);
@@ -380,8 +421,6 @@ __global__ void __launch_bounds__(MAXT, 3) collapse_kernel(const ColArgs a) {
     const Geo g1 = s_geo[1];
 
     // ---- last expansion fused with add-back, store and ROI sums -------------------------------
-    Tile<KMAX, F32OUT, U8OUT> tl(a);
-    tl.t = t; tl.x0 = x0; tl.x1 = x1; tl.y0 = y0; tl.y1 = y1;
     tl.l1 = smf + g1.off - g1.r0 * g1.rs - g1.c0;
     tl.l1_rs = g1.rs; tl.l1_ps = g1.ps;
     tl.stage = smf + a.stage_off + (tid >> 5) * 768;
@@ -400,9 +439,9 @@ __global__ void __launch_bounds__(MAXT, 3) collapse_kernel(const ColArgs a) {
         }
     }
     if (a.vec_ok) {
-        if (any_hit) tl.template run<true, true>(); else tl.template run<false, true>();
+        if (any_hit) tl.template run<true, true>(wfirst); else tl.template run<false, true>(wfirst);
     } else {
-        if (any_hit) tl.template run<true, false>(); else tl.template run<false, false>();
+        if (any_hit) tl.template run<true, false>(wfirst); else tl.template run<false, false>(wfirst);
     }
 
     if (KMAX > 0 && any_hit) {       // block-uniform
