@@ -30,6 +30,7 @@
 //     -> fixed-order finalize kernel.  No atomics: results are run-to-run identical.
 #include "common.cuh"
 #include <stdlib.h>
+#include <vector>
 
 namespace {
 
@@ -42,7 +43,20 @@ struct Geo {                  // storage of one level's region: planar, apron of
     int off;                  // float offset of plane 0 in dynamic smem
 };
 
+// Level-L region + storage geometry per tile position (independent of the frame), host-built
+// and served from constant memory: the gather that heads every tile's critical path needs it
+// before anything else, and a constant-cache hit costs no DRAM round trip.
+struct TileL {
+    int ra, rb, ca, cb;
+    int c0, r0, rs, ps;
+    unsigned inv_nc3;         // magic reciprocal of 3 * (cb - ca + 3)
+    int pad[3];
+};
+constexpr int MAX_CONST_TILES = 1024;
+__constant__ TileL c_tileL[MAX_CONST_TILES];
+
 struct ColArgs {
+    int use_const_tiles;      // tiles_x * tiles_y <= MAX_CONST_TILES and c_tileL is valid for this launch
     const float* lvl;
     const uint8_t* frames;
     float* out_f32;
@@ -352,7 +366,13 @@ __global__ void __launch_bounds__(MAXT, 3) collapse_kernel(const ColArgs a) {
     __shared__ Geo s_geo[VHR_MAX_LEVELS + 1];
     Geo qL;
     int raL, rbL, caL, cbL;
-    {
+    unsigned invL;
+    if (a.use_const_tiles) {
+        const TileL q = c_tileL[tile];
+        raL = q.ra; rbL = q.rb; caL = q.ca; cbL = q.cb;
+        qL.c0 = q.c0; qL.r0 = q.r0; qL.rs = q.rs; qL.ps = q.ps; qL.off = 0;
+        invL = q.inv_nc3;
+    } else {
         int ra = y0, rb = y1 - 1, ca = x0, cb = x1 - 1;
         for (int l = 1; l <= L; ++l) {
             ra = max(0, (ra >> 1) - 1);
@@ -366,6 +386,7 @@ __global__ void __launch_bounds__(MAXT, 3) collapse_kernel(const ColArgs a) {
         qL.rs = ((cb + 8 - qL.c0) + 3) & ~3;
         qL.ps = (rb - ra + 5) * qL.rs;
         qL.off = 0;
+        invL = 0xFFFFFFFFu / (unsigned)((cb - ca + 3) * 3) + 1u;
     }
     if (tid >= 1 && tid <= L) {
         int ra = y0, rb = y1 - 1, ca = x0, cb = x1 - 1;
@@ -389,7 +410,7 @@ __global__ void __launch_bounds__(MAXT, 3) collapse_kernel(const ColArgs a) {
     {
         const Geo q = qL;
         const int nr = rbL - raL + 3, nc3 = (cbL - caL + 3) * 3;
-        const unsigned inv = 0xFFFFFFFFu / (unsigned)nc3 + 1u;
+        const unsigned inv = invL;
         const float* src = a.lvl + ((size_t)t * a.h[L] * a.w[L]) * 3;
         for (int idx = tid; idx < nr * nc3; idx += nthreads) {
             const int r = (int)__umulhi((unsigned)idx, inv), j = idx - r * nc3;
@@ -570,6 +591,38 @@ extern "C" int vhr_collapse_addback_roi(vhr_ctx* ctx, const float* d_level, cons
     if ((long long)smem > ctx->smem_optin) {
         vhr_set_error(ctx, "collapse: tile needs %zu bytes of shared memory (> %d)", smem, ctx->smem_optin);
         return VHR_ERR_UNSUPPORTED;
+    }
+    // level-L geometry per tile position -> constant memory (rebuilt only when the shape changes)
+    {
+        static long long s_key = -1;                 // c_tileL is per module: one key for all contexts
+        const long long key = ((long long)W << 40) ^ ((long long)H << 20) ^ ((long long)levels << 16) ^ ((long long)TW << 4) ^ (long long)TH;
+        const int ntile = a.tiles_x * a.tiles_y;
+        a.use_const_tiles = ntile <= MAX_CONST_TILES;
+        if (a.use_const_tiles && s_key != key) {
+            std::vector<TileL> tab((size_t)ntile);
+            for (int by = 0; by < a.tiles_y; ++by)
+                for (int bx = 0; bx < a.tiles_x; ++bx) {
+                    const int x0 = bx * TW, x1 = (W < x0 + TW) ? W : x0 + TW, y0 = by * TH, y1 = (H < y0 + TH) ? H : y0 + TH;
+                    int ra = y0, rb = y1 - 1, ca = x0, cb = x1 - 1;
+                    for (int l = 1; l <= levels; ++l) {
+                        ra = (ra >> 1) - 1 < 0 ? 0 : (ra >> 1) - 1;
+                        rb = (rb >> 1) + 1 > a.h[l] - 1 ? a.h[l] - 1 : (rb >> 1) + 1;
+                        ca = (ca >> 1) - 1 < 0 ? 0 : (ca >> 1) - 1;
+                        cb = (cb >> 1) + 1 > a.w[l] - 1 ? a.w[l] - 1 : (cb >> 1) + 1;
+                    }
+                    TileL& q = tab[(size_t)by * a.tiles_x + bx];
+                    memset(&q, 0, sizeof(q));
+                    q.ra = ra; q.rb = rb; q.ca = ca; q.cb = cb;
+                    q.c0 = 4 * (ca >> 2) - 5;
+                    q.r0 = ra - 2;
+                    q.rs = ((cb + 8 - q.c0) + 3) & ~3;
+                    q.ps = (rb - ra + 5) * q.rs;
+                    q.inv_nc3 = 0xFFFFFFFFu / (unsigned)((cb - ca + 3) * 3) + 1u;
+                }
+            VHR_CHECK_CUDA(ctx, cudaDeviceSynchronize());     // launches still reading the previous table
+            VHR_CHECK_CUDA(ctx, cudaMemcpyToSymbol(c_tileL, tab.data(), tab.size() * sizeof(TileL)));
+            s_key = key;
+        }
     }
     a.vec_ok = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_frames) & 3) == 0) &&
                (!d_out_f32 || (reinterpret_cast<uintptr_t>(d_out_f32) & 15) == 0) &&
