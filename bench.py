@@ -207,7 +207,8 @@ def run_gpu(args):
     rects = torch.as_tensor(np.tile(rect, (T, 1, 1)).astype(np.int32), device=dev)
     out = torch.empty((T, H, W, 3), dtype=torch.float32, device=dev)
     lvl = torch.empty((T, hl, wl, 3), dtype=torch.float32, device=dev)
-    starts, lens = [0], [T]
+    starts = torch.zeros(1, dtype=torch.int32, device=dev)      # BPM window list lives on the device
+    lens = torch.full((1,), T, dtype=torch.int32, device=dev)
     torch.cuda.synchronize()
 
     stream = torch.cuda.current_stream(dev)
@@ -225,7 +226,7 @@ def run_gpu(args):
         _, _, means = eng.collapse(lvl, fr, LEVELS, out_f32=out, out_u8=False, rects=rects)
         if timed: e[3].record(stream)
         bpm, kbin = eng.bpm_fft(means[:, 0, 1].contiguous(), starts, lens, fps, ANALYSIS_BAND,
-                                detrend=vhr.DETREND_F32, mode=vhr.FFT_ANALYSIS)
+                                detrend=vhr.DETREND_F32, mode=vhr.FFT_ANALYSIS, max_len=T)
         if timed:
             e[4].record(stream)
             for name, a, b in (("pyrdown", 0, 1), ("bandpass", 1, 2), ("collapse", 2, 3), ("bpm", 3, 4)):
@@ -298,7 +299,7 @@ def run_gpu(args):
 
         def e2e_step():
             means = eng.evm_roi_host(fr_np, fps, rects_np, LEVELS, F_LO, F_HI, ALPHA)      # H2D + kernels + D2H
-            bpm, _ = eng.bpm_fft(means[:, 0, 1], starts, lens, fps, ANALYSIS_BAND, detrend=vhr.DETREND_F32)
+            bpm, _ = eng.bpm_fft(means[:, 0, 1], starts, lens, fps, ANALYSIS_BAND, detrend=vhr.DETREND_F32, max_len=T)
             return float(bpm[0].item())                                                    # D2H of the result
 
         e2e_step()

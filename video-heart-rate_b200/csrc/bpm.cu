@@ -116,6 +116,28 @@ __device__ __forceinline__ double dft_power(const double* x, int n, int k, const
     return re * re + im * im;
 }
 
+// same sum with the 32 lanes of a warp striding over the samples (butterfly reduction: every
+// lane ends with the same value)
+__device__ __forceinline__ double dft_power_warp(const double* x, int n, int k, const double2* tw) {
+    const int lane = threadIdx.x & 31;
+    double re = 0., im = 0.;
+    const int dk = (int)(((long long)k * 32) % n);
+    int m = (int)(((long long)k * lane) % n);
+    for (int i = lane; i < n; i += 32) {
+        const double2 w = tw[m];
+        re = fma(x[i], w.x, re);
+        im = fma(-x[i], w.y, im);
+        m += dk;
+        if (m >= n) m -= n;
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        re += __shfl_xor_sync(0xffffffffu, re, d);
+        im += __shfl_xor_sync(0xffffffffu, im, d);
+    }
+    return re * re + im * im;
+}
+
 struct ArgMax {
     double v;
     int k;
@@ -184,10 +206,11 @@ __global__ void __launch_bounds__(BT) bpm_fft_kernel(const FftArgs a) {
         ArgMax mine;
         mine.v = 0.;
         mine.k = -1;
-        for (int k = 1 + threadIdx.x; k <= kmax; k += BT) {
+        // one warp per bin (long windows: a single window must not serialise 1800 samples per thread)
+        for (int k = 1 + (int)(threadIdx.x >> 5); k <= kmax; k += BT / 32) {
             const double f = np_freq(k, n, a.fs);
-            if (f >= a.f_lo && f <= a.f_hi) {
-                const double p = dft_power(x, n, k, tw);
+            if (f >= a.f_lo && f <= a.f_hi) {           // warp-uniform
+                const double p = dft_power_warp(x, n, k, tw);
                 if (mine.k < 0 || p > mine.v) { mine.v = p; mine.k = k; }
             }
         }

@@ -231,14 +231,14 @@ class Engine:
         return mask
 
     # ------------------------------------------------------------------ BPM
-    def bpm_fft(self, trace, starts, lens, fs: float, band, detrend: int = DETREND_NONE, mode: int = FFT_ANALYSIS):
+    def bpm_fft(self, trace, starts, lens, fs: float, band, detrend: int = DETREND_NONE, mode: int = FFT_ANALYSIS,
+                max_len: Optional[int] = None):
         """trace float64 (n,) or (n,C); windows (start,len) -> (bpm float64 (n_win), bin int32)."""
         torch = _torch()
         tr = self._dev(trace, torch.float64)
         if tr.ndim == 1:
             tr = tr[:, None].contiguous()
         n, Cc = tr.shape
-        lens_np = np.asarray(lens if not isinstance(lens, torch.Tensor) else lens.cpu(), dtype=np.int64)
         st = self._dev(starts, torch.int32)
         ln = self._dev(lens, torch.int32)
         nw = st.numel()
@@ -246,7 +246,10 @@ class Engine:
         kbin = torch.empty(nw, dtype=torch.int32, device=self.tdev)
         if nw == 0:
             return bpm, kbin
-        max_len = int(min(n, max(1, lens_np.max())))
+        if max_len is None:      # device-resident window lists: pass max_len to avoid a D2H sync
+            lens_np = np.asarray(lens if not isinstance(lens, torch.Tensor) else lens.cpu(), dtype=np.int64)
+            max_len = int(lens_np.max())
+        max_len = int(min(n, max(1, max_len)))
         self._check(self.lib.vhr_bpm_fft(self.ctx, self._p(tr), n, Cc, self._p(st), self._p(ln), nw, max_len,
                                          float(fs), float(band[0]), float(band[1]), detrend, mode, self._p(bpm),
                                          self._p(kbin), self._stream()), "vhr_bpm_fft")
