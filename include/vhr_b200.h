@@ -132,8 +132,10 @@ int vhr_poly_mask(vhr_ctx* ctx, int T, int H, int W, const int32_t* d_poly,
  * (NaN where the reference returns None), d_bin int32 (n_win) = chosen FFT/rfft bin.
  *
  * detrend modes: 0 none; 1 float64 mean (rppg_VIDEO.py:399); 2 cast to float32, subtract
- * the float32 pairwise mean, as green_avg.py:42-43 does before estimate_bpm. */
-enum { VHR_DETREND_NONE = 0, VHR_DETREND_F64 = 1, VHR_DETREND_F32 = 2 };
+ * the float32 pairwise mean, as green_avg.py:42-43 does before estimate_bpm;
+ * 3 float32 z-score (x - mean) / std (green_avg_psd_plot.py:174-175).
+ */
+enum { VHR_DETREND_NONE = 0, VHR_DETREND_F64 = 1, VHR_DETREND_F32 = 2, VHR_DETREND_ZSCORE_F32 = 3 };
 /* analysis/utils/estimate_bpm.py:12-65 (mode 0: |X| over freqs>0, N>=8 required) and
  * rppg_VIDEO.py:129-147 (mode 1: mask on signed fftfreq, no length floor). */
 enum { VHR_FFT_ANALYSIS = 0, VHR_FFT_VIDEO = 1 };
@@ -166,6 +168,23 @@ int vhr_bpm_welch(vhr_ctx* ctx, const double* d_trace, int n_trace,
  * updated (zero it for live_sos_init / live_sos_reset). */
 int vhr_sos_causal(vhr_ctx* ctx, const double* d_x, int n, const double* h_sos, int n_sec,
                    double* d_state, double* d_y, void* stream);
+
+/* ---- analysis-harness degradations and metric ---------------------------
+ * Additive noise: clip(float(frame) + noise, 0, 255) truncated to uint8 -- analysis/degradation/
+ * colour_noise.py:11-24.  The noise is a counter-based hash (std = noise_gain_q8 * 147.8 / 256
+ * LSB) of (seed, clip, t0 + t, byte index) so the CPU oracle regenerates it bit for bit; the
+ * reference draws np.random.normal.  In place allowed. */
+int vhr_degrade_noise_u8(vhr_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int T, int H, int W,
+                         int noise_gain_q8, uint32_t seed, uint32_t clip, int t0, void* stream);
+/* Bit-depth quantisation: scale = 256 // 2**bits; (x // scale) * scale -- analysis/degradation/
+ * colour_quantisation.py:12-25 (bits > 8 gives all zeros, like NumPy's uint8 // 0). */
+int vhr_degrade_quantise_u8(vhr_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, long long n, int bits,
+                            void* stream);
+/* Step-hold truth alignment + MAE: analysis/utils/video_io.py:80-106 (searchsorted side='right'
+ * minus 1, clipped) and analysis/metrics/mae.py:32-36.  d_meas float64 (m,2) [t_sec, bpm];
+ * d_aligned float64 (m) truth HR per measurement; d_mae float64 (1). */
+int vhr_align_mae(vhr_ctx* ctx, const double* d_truth_t, const double* d_truth_hr, int n_truth,
+                  const double* d_meas, int m, double* d_aligned, double* d_mae, void* stream);
 
 /* ---- host-buffer convenience (the reference-facing call: NumPy arrays in and out) -------
  * Whole EVM + ROI path on one clip held in HOST memory: H2D of the frames, the three EVM

@@ -161,11 +161,42 @@ def gen_bpm(out):
     print("bpm:", i, "traces")
 
 
+def gen_metrics(out):
+    """colour_quantisation.quantise_colour, video_io.interpolate_hr_to_frames, mae.py:32-36."""
+    import pandas as pd
+    Q = ref_loader.load_functions("analysis/degradation/colour_quantisation.py", ["quantise_colour"])
+    Vio = ref_loader.load_functions("analysis/utils/video_io.py", ["interpolate_hr_to_frames"], extra_ns={"pd": pd})
+    rng = np.random.default_rng(99)
+    rec = {}
+    frame = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    rec["q_frame"] = frame
+    for bits in (9, 8, 7, 6, 5, 4):                      # COLOUR_DEPTHS, colour_quantisation.py:9
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            rec[f"q_bits_{bits}"] = Q["quantise_colour"](frame, bits)
+    for j in range(4):
+        n, m = int(rng.integers(5, 60)), int(rng.integers(10, 400))
+        tt = np.sort(rng.uniform(0, 60, n))
+        if j == 1:
+            tt = tt + 5.0                                   # measurements before the first truth sample
+        th = rng.uniform(50, 120, n)
+        meas = np.column_stack([np.sort(rng.uniform(0, 70, m)), rng.uniform(40, 200, m)])
+        truth = pd.DataFrame({"timestamp": tt, "heart_rate": th})
+        aligned = Vio["interpolate_hr_to_frames"](truth, meas)
+        mae = float(np.mean(np.abs(meas[:, 1].astype(float) - aligned[:, 1].astype(float))))   # mae.py:32-36
+        rec[f"m_tt_{j}"] = tt; rec[f"m_th_{j}"] = th; rec[f"m_meas_{j}"] = meas
+        rec[f"m_aligned_{j}"] = aligned; rec[f"m_mae_{j}"] = np.float64(mae)
+    rec["n_m"] = 4
+    np.savez_compressed(os.path.join(out, "metrics.npz"), **rec)
+    print("metrics: quantise x6, alignment x4")
+
+
 def main():
     if not ref_loader.available():
         raise SystemExit("reference tree not found; golden vectors can only be made in the build container")
     gen_roi(HERE)
     gen_bpm(HERE)
+    gen_metrics(HERE)
 
 
 if __name__ == "__main__":

@@ -337,3 +337,42 @@ def test_evm_roi_host_matches_device_path(vhr, eng):
     import torch
     r = eng.evm(torch.as_tensor(fr, device=eng.tdev), 10.0, 3, 0.7, 4.0, 50.0, rects=rects)
     np.testing.assert_array_equal(means, r["roi_mean"].cpu().numpy())       # same kernels, deterministic
+
+
+# ------------------------------------------------------------------- degradations / metric
+def test_degradations_and_mae(vhr, eng, golden_dir):
+    import torch
+    from oracle import degrade as odeg
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    fr = torch.as_tensor(g["q_frame"][None], device=eng.tdev)
+    for bits in (9, 8, 7, 6, 5, 4):
+        np.testing.assert_array_equal(eng.degrade_quantise(fr, bits).cpu().numpy()[0], g[f"q_bits_{bits}"])
+    rng = np.random.default_rng(12)
+    frames = rng.integers(0, 256, (5, 33, 47, 3), dtype=np.uint8)
+    fd = torch.as_tensor(frames, device=eng.tdev)
+    for sigma in (5, 10, 20, 40):
+        got = eng.degrade_noise(fd, sigma, seed=3, clip=1, t0=2).cpu().numpy()
+        np.testing.assert_array_equal(got, odeg.add_noise(frames, sigma, seed=3, clip=1, t0=2))
+    for j in range(int(g["n_m"])):
+        aligned, mae = eng.align_mae(g[f"m_tt_{j}"], g[f"m_th_{j}"], g[f"m_meas_{j}"])
+        np.testing.assert_array_equal(aligned.cpu().numpy(), g[f"m_aligned_{j}"][:, 1])
+        assert mae == float(g[f"m_mae_{j}"])
+
+
+def test_green_avg_psd_variant(vhr, eng):
+    """green_avg_psd_plot.py variant (z-score + Butterworth sosfiltfilt + periodogram): identical BPM
+    per frame against the oracle restatement of :173-183 / :34-63."""
+    from video_heart_rate_b200.pipeline import green_avg_psd_series
+    rng = np.random.default_rng(21)
+    for fps, n in ((30.0, 400), (5.0, 80), (29.97, 330)):
+        t = np.arange(n) / fps
+        g = 140 + 0.8 * np.sin(2 * np.pi * 1.45 * t) + 0.3 * rng.standard_normal(n) + 0.05 * t
+        got = green_avg_psd_series(eng, g, fps)
+        wl = int(round(10.0 * fps))
+        exp = np.full(n, np.nan)
+        for i in range(n):
+            w = g[max(0, i + 1 - wl): i + 1]
+            if len(w) >= wl:
+                exp[i] = obpm.psd_plot_estimate(w, fps)[0]
+        np.testing.assert_array_equal(got[:, 1], exp)
+        np.testing.assert_array_equal(got[:, 0], np.arange(n) * (1 / fps))

@@ -230,3 +230,25 @@ def test_green_avg_series_matches_reference_loop():
                 bp.append(b)
         ours, _ = obpm.green_avg_series(green, fps)
         np.testing.assert_array_equal(ours, np.column_stack([ts, bp]))
+
+
+# ------------------------------------------------------------------- degradations / metric
+def test_degrade_and_metric_match_reference_golden(golden_dir):
+    from oracle import degrade as odeg
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    for bits in (9, 8, 7, 6, 5, 4):
+        np.testing.assert_array_equal(odeg.quantise_colour(g["q_frame"], bits), g[f"q_bits_{bits}"])
+    for j in range(int(g["n_m"])):
+        al = odeg.align_truth(g[f"m_tt_{j}"], g[f"m_th_{j}"], g[f"m_meas_{j}"])
+        np.testing.assert_array_equal(al, g[f"m_aligned_{j}"])
+        assert odeg.mae(g[f"m_tt_{j}"], g[f"m_th_{j}"], g[f"m_meas_{j}"]) == float(g[f"m_mae_{j}"])
+
+
+def test_noise_statistics_match_reference_distribution():
+    """Our hash noise has the mean / std the reference's np.random.normal(0, sigma) has."""
+    from oracle import degrade as odeg
+    fr = np.full((4, 64, 64, 3), 128, dtype=np.uint8)
+    for sigma in (5, 10, 20, 40):                       # NOISE_LEVELS, colour_noise.py:8
+        d = odeg.add_noise(fr, sigma, seed=1).astype(np.float64) - 128.0
+        assert abs(d.mean() + 0.5) < 0.3                # astype(uint8) truncation biases by -0.5
+        assert abs(d.std() - sigma) < 0.06 * sigma + 0.3

@@ -46,6 +46,10 @@ SIGNATURES = {
                               c_int, c_int, c_void_p, c_int, c_double, c_void_p, c_void_p, c_void_p, c_int,
                               c_void_p]),
     "vhr_sos_causal": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "vhr_degrade_noise_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, C.c_uint32, C.c_uint32,
+                                     c_int, c_void_p]),
+    "vhr_degrade_quantise_u8": (c_int, [c_void_p, c_void_p, c_void_p, C.c_longlong, c_int, c_void_p]),
+    "vhr_align_mae": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "vhr_evm_roi_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_double, c_double,
                                  c_float, c_void_p, c_int, c_void_p, c_void_p]),
 }

@@ -12,6 +12,7 @@
 //                  initial state)
 //   vhr_sos_causal rppg_LIVESTREAM.py:226-251 live_sos_push (sosfilt with carried state)
 #include "common.cuh"
+#include "pairwise.cuh"
 #include <math.h>
 
 namespace {
@@ -22,63 +23,6 @@ constexpr int MAXTAPS = 128;
 constexpr int MAXCOEF = (MAXSEC * 6 > MAXTAPS) ? MAXSEC * 6 : MAXTAPS;
 
 __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7FF8000000000000ll); }
-
-// numpy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src), which is what np.mean /
-// np.nanmean of a contiguous float vector evaluates.  The recursion (split at n/2 rounded
-// down to a multiple of 8 until blocks are <= 128 long) is run with an explicit stack: device
-// recursion would need more than the default per-thread stack.
-__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
-__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
-
-template <typename F>
-__device__ F pairwise_leaf(const F* a, int n) {
-    if (n < 8) {
-        F res = (F)0;
-        for (int i = 0; i < n; ++i) res = add_rn(res, a[i]);
-        return res;
-    }
-    F r[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = a[j];
-    int i;
-    for (i = 8; i < n - (n % 8); i += 8) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = add_rn(r[j], a[i + j]);
-    }
-    F res = add_rn(add_rn(add_rn(r[0], r[1]), add_rn(r[2], r[3])), add_rn(add_rn(r[4], r[5]), add_rn(r[6], r[7])));
-    for (; i < n; ++i) res = add_rn(res, a[i]);
-    return res;
-}
-
-template <typename F>
-__device__ F pairwise_sum(const F* a, int n) {
-    if (n <= 128) return pairwise_leaf(a, n);
-    int s_off[40], s_len[40];
-    bool s_comb[40];
-    F vals[40];
-    int sp = 0, vp = 0;
-    s_off[sp] = 0; s_len[sp] = n; s_comb[sp] = false; ++sp;
-    while (sp > 0) {
-        --sp;
-        const int off = s_off[sp], len = s_len[sp];
-        if (s_comb[sp]) {
-            const F r = vals[--vp];
-            const F l = vals[--vp];
-            vals[vp++] = add_rn(l, r);
-        } else if (len <= 128) {
-            vals[vp++] = pairwise_leaf(a + off, len);
-        } else {
-            int n2 = len / 2;
-            n2 -= n2 % 8;
-            s_off[sp] = off; s_len[sp] = len; s_comb[sp] = true; ++sp;              // combine after both halves
-            s_off[sp] = off + n2; s_len[sp] = len - n2; s_comb[sp] = false; ++sp;    // right half (evaluated second)
-            s_off[sp] = off; s_len[sp] = n2; s_comb[sp] = false; ++sp;               // left half (evaluated first)
-        }
-    }
-    return vals[0];
-}
-__device__ __forceinline__ float pairwise_sum_f32(const float* a, int n) { return pairwise_sum<float>(a, n); }
-__device__ __forceinline__ double pairwise_sum_f64(const double* a, int n) { return pairwise_sum<double>(a, n); }
 
 // frequency of bin k exactly as numpy.fft.fftfreq / rfftfreq compute it:
 //   val = 1.0 / (n * d), d = 1 / fs ; f = k * val
@@ -99,6 +43,14 @@ __device__ void detrend_window(double* x, float* xf, int n, int mode) {
         for (int i = 0; i < n; ++i) xf[i] = (float)x[i];
         const float m = __fdiv_rn(pairwise_sum_f32(xf, n), (float)n);
         for (int i = 0; i < n; ++i) x[i] = (double)__fsub_rn(xf[i], m);
+    } else if (mode == VHR_DETREND_ZSCORE_F32) {
+        // (sig - np.mean(sig)) / np.std(sig) on a float32 vector (green_avg_psd_plot.py:174-175):
+        // np.std = sqrt(pairwise_sum((x - mean)^2) / n), every step in float32
+        for (int i = 0; i < n; ++i) xf[i] = (float)x[i];
+        const float m = __fdiv_rn(pairwise_sum_f32(xf, n), (float)n);
+        for (int i = 0; i < n; ++i) { const float d = __fsub_rn(xf[i], m); x[i] = (double)d; xf[i] = __fmul_rn(d, d); }
+        const float sd = __fsqrt_rn(__fdiv_rn(pairwise_sum_f32(xf, n), (float)n));
+        for (int i = 0; i < n; ++i) x[i] = (double)__fdiv_rn((float)x[i], sd);
     }
 }
 
@@ -460,7 +412,7 @@ extern "C" int vhr_bpm_fft(vhr_ctx* ctx, const double* d_trace, int n_trace, int
     VHR_REQUIRE(ctx, ctx != nullptr, "null context");
     VHR_REQUIRE(ctx, d_trace && d_start && d_len && d_bpm && d_bin, "null pointer");
     VHR_REQUIRE(ctx, C >= 1 && fs > 0, "bad arguments");
-    VHR_REQUIRE(ctx, detrend >= 0 && detrend <= 2 && (mode == 0 || mode == 1), "bad detrend/mode");
+    VHR_REQUIRE(ctx, detrend >= 0 && detrend <= 3 && (mode == 0 || mode == 1), "bad detrend/mode");
     int rc = check_windows(ctx, n_trace, n_win);
     if (rc != VHR_OK) return rc;
     FftArgs a;
@@ -485,7 +437,7 @@ extern "C" int vhr_bpm_welch(vhr_ctx* ctx, const double* d_trace, int n_trace, c
     VHR_REQUIRE(ctx, ctx != nullptr, "null context");
     VHR_REQUIRE(ctx, d_trace && d_start && d_len && d_bpm && d_bin, "null pointer");
     VHR_REQUIRE(ctx, fs > 0 && welch_seconds > 0, "bad arguments");
-    VHR_REQUIRE(ctx, detrend >= 0 && detrend <= 2, "bad detrend");
+    VHR_REQUIRE(ctx, detrend >= 0 && detrend <= 3, "bad detrend");
     VHR_REQUIRE(ctx, max_len >= 1 && max_len <= n_trace, "max_len must be 1..n_trace");
     int rc = check_windows(ctx, n_trace, n_win);
     if (rc != VHR_OK) return rc;

@@ -11,7 +11,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["api.cu", "synth.cu", "pyrdown.cu", "pyrdown_fast.cu", "bandpass.cu", "collapse.cu", "roi.cu", "bpm.cu", "hostpath.cu"]
+SOURCES = ["api.cu", "synth.cu", "pyrdown.cu", "pyrdown_fast.cu", "bandpass.cu", "collapse.cu", "roi.cu", "bpm.cu", "degrade.cu", "hostpath.cu"]
 LIB = os.path.join(HERE, "libvhr_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
@@ -28,7 +28,7 @@ def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(HERE, s) for s in SOURCES] + [os.path.join(HERE, "common.cuh"),
+    deps = [os.path.join(HERE, s) for s in SOURCES] + [os.path.join(HERE, "common.cuh"), os.path.join(HERE, "pairwise.cuh"),
                                                         os.path.join(HERE, "..", "..", "include", "vhr_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 

@@ -14,7 +14,7 @@ import numpy as np
 from . import _lib
 from .synth import SynthSpec
 
-DETREND_NONE, DETREND_F64, DETREND_F32 = 0, 1, 2
+DETREND_NONE, DETREND_F64, DETREND_F32, DETREND_ZSCORE_F32 = 0, 1, 2, 3
 FFT_ANALYSIS, FFT_VIDEO = 0, 1
 FILT_NONE, FILT_SOS, FILT_FIR = 0, 1, 2
 
@@ -293,6 +293,42 @@ class Engine:
                                             sos.shape[0], self._p(state), self._p(y), self._stream()),
                     "vhr_sos_causal")
         return y
+
+
+    # ------------------------------------------------------------------ degradations / metric
+    def degrade_noise(self, frames, sigma: float, seed: int = 0, clip: int = 0, t0: int = 0, out=None):
+        """colour_noise.add_gaussian_noise on device (hash noise of std ``sigma`` LSB)."""
+        torch = _torch()
+        assert frames.dtype == torch.uint8 and frames.is_cuda and frames.is_contiguous()
+        T, H, W, _ = frames.shape
+        out = torch.empty_like(frames) if out is None else out
+        gain = int(round(sigma * 256.0 / 147.80053225049948))
+        self._check(self.lib.vhr_degrade_noise_u8(self.ctx, self._p(frames), self._p(out), T, H, W, gain,
+                                                  seed & 0xFFFFFFFF, clip & 0xFFFFFFFF, t0, self._stream()),
+                    "vhr_degrade_noise_u8")
+        return out
+
+    def degrade_quantise(self, frames, bits: int, out=None):
+        """colour_quantisation.quantise_colour on device."""
+        torch = _torch()
+        assert frames.dtype == torch.uint8 and frames.is_cuda and frames.is_contiguous()
+        out = torch.empty_like(frames) if out is None else out
+        self._check(self.lib.vhr_degrade_quantise_u8(self.ctx, self._p(frames), self._p(out), frames.numel(), int(bits),
+                                                     self._stream()), "vhr_degrade_quantise_u8")
+        return out
+
+    def align_mae(self, truth_t, truth_hr, measured):
+        """Step-hold truth alignment + MAE -> (aligned_hr (m,) tensor, mae float)."""
+        torch = _torch()
+        tt = self._dev(truth_t, torch.float64).reshape(-1)
+        th = self._dev(truth_hr, torch.float64).reshape(-1)
+        me = self._dev(measured, torch.float64).reshape(-1, 2)
+        m = me.shape[0]
+        aligned = torch.empty(m, dtype=torch.float64, device=self.tdev)
+        mae = torch.empty(1, dtype=torch.float64, device=self.tdev)
+        self._check(self.lib.vhr_align_mae(self.ctx, self._p(tt), self._p(th), tt.numel(), self._p(me), m,
+                                           self._p(aligned), self._p(mae), self._stream()), "vhr_align_mae")
+        return aligned, float(mae.item())
 
 
 _default: dict = {}

@@ -10,7 +10,8 @@ from __future__ import annotations
 import numpy as np
 
 from . import host
-from .engine import (DETREND_F32, DETREND_F64, DETREND_NONE, FFT_ANALYSIS, FILT_FIR, FILT_NONE, FILT_SOS, Engine)
+from .engine import (DETREND_F32, DETREND_F64, DETREND_NONE, DETREND_ZSCORE_F32, FFT_ANALYSIS, FILT_FIR, FILT_NONE, FILT_SOS,
+                     Engine)
 
 VIDEO_BAND = (0.7, 2.0)                 # rppg_VIDEO.py:33-34
 LIVE_BAND = (40 / 60, 150 / 60)         # rppg_LIVESTREAM.py:34-35
@@ -65,6 +66,41 @@ def green_avg_measure(eng: Engine, frames, fps: float, landmarks, valid=None, ch
     ok = ~np.isnan(bpm)                                   # `if bpm is not None` (green_avg.py:47)
     ts = idx_all[fi] * (1 / fps)                          # ts = i * (1 / fps)  (green_avg.py:48)
     return np.column_stack([ts[ok], bpm[ok]])
+
+
+def green_avg_psd_series(eng: Engine, green, fps: float, band=ANALYSIS_BAND, window_s: float = 10.0, acq_s: float = 10.0,
+                         order: int = 2) -> np.ndarray:
+    """The BPM series of analysis/measurement/green_avg_psd_plot.py:160-185 given the per-frame green
+    means: rolling ``int(round(window_s*fps))`` window, NaN rows until ``int(round(acq_s*fps))`` samples
+    are in, then float32 z-score -> Butterworth(order) sosfiltfilt with clamped edges (:34-43) ->
+    periodogram peak (:46-63).  -> (T,2) [t_sec, bpm]."""
+    import scipy.signal as sp
+    import torch
+    g = green if isinstance(green, torch.Tensor) else torch.as_tensor(np.asarray(green, dtype=np.float64), device=eng.tdev)
+    n = int(g.numel())
+    window_len, acq = int(round(window_s * fps)), int(round(acq_s * fps))
+    i = np.arange(n, dtype=np.int64)
+    length = np.minimum(i + 1, window_len)
+    keep = length >= acq
+    ts = i * (1 / fps)
+    out = np.column_stack([ts, np.full(n, np.nan)])
+    if not keep.any():
+        return out
+    st = (i + 1 - length)[keep].astype(np.int32)
+    ln = length[keep].astype(np.int32)
+    nyq = 0.5 * fps
+    low, high = max(1e-6, band[0] / nyq), min(0.999, band[1] / nyq)
+    if high > low:
+        sos = sp.butter(order, [low, high], btype="band", output="sos")
+        _, _, filt = eng.bpm_welch(g, st, ln, fps, band, detrend=DETREND_ZSCORE_F32, filt_kind=FILT_SOS, coef=sos,
+                                   want_filtered=True)
+    else:
+        _, _, filt = eng.bpm_welch(g, st, ln, fps, band, detrend=DETREND_ZSCORE_F32, filt_kind=FILT_NONE, want_filtered=True)
+    nw, ml = filt.shape
+    starts2 = (np.arange(nw, dtype=np.int64) * ml).astype(np.int32)
+    bpm, _ = eng.bpm_fft(filt.reshape(-1), starts2, ln, fps, band, detrend=DETREND_NONE, mode=FFT_ANALYSIS, max_len=ml)
+    out[keep, 1] = bpm.cpu().numpy()
+    return out
 
 
 def video_trace(eng: Engine, frames_bgr, landmarks, overdraw: bool = True, channel: int = 1):
