@@ -376,3 +376,15 @@ def test_green_avg_psd_variant(vhr, eng):
                 exp[i] = obpm.psd_plot_estimate(w, fps)[0]
         np.testing.assert_array_equal(got[:, 1], exp)
         np.testing.assert_array_equal(got[:, 0], np.arange(n) * (1 / fps))
+
+
+# ------------------------------------------------------------------- BASELINE configs (reduced)
+def test_config_runners_reduced(vhr, eng):
+    """tools/run_configs.py: c1 in full (CPU-path config: bit-exact trace, identical BPM triplets,
+    FIR raises like the reference) and a 20-window slice of the c5 sweep (MAE within one bin)."""
+    from tools import run_configs as rc
+    r1 = rc.run_c1(eng, vhr)
+    assert r1["trace_bit_exact"] and r1["bpm_identical"] and r1["windows"] == 100
+    assert r1["bpm_butter_last"] == pytest.approx(73.3333, abs=1e-3) and r1["evm_bpm"] == 72.0
+    r5 = rc.run_c5(eng, vhr, n=20)
+    assert r5["windows"] == 20 and r5["nan_windows"] == 0 and r5["mae_bpm"] <= 3.0

@@ -1,0 +1,190 @@
+#!/usr/bin/env python
+"""Run the BASELINE.json configurations that are not the bench line (c4 = bench.py):
+
+    python tools/run_configs.py --config c1     256x144 5 FPS 30 s, rppg_VIDEO-style path vs the CPU oracle
+    python tools/run_configs.py --config c2     one 1280x720 30 FPS 60 s clip: frames/s + BPM
+    python tools/run_configs.py --config c3     640x480 30 FPS stream, 10 s window / 1 s hop: per-window latency
+    python tools/run_configs.py --config c5     degradation sweep (resolution x frame rate x noise), MAE vs truth
+    torchrun --nproc-per-node N tools/run_configs.py --config c5     (windows sharded by cost, one final gather)
+
+One JSON line per config on rank 0.  Synthetic clips (seeded, pulse of known frequency).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+LEVELS, BAND, ALPHA = 4, (0.7, 4.0), 50.0
+RES = {144: 256, 240: 426, 360: 640, 480: 854, 720: 1280, 1080: 1920}     # 16:9 widths
+FPS = [5, 10, 15, 25, 30]                                                   # temporal_resolution.py:7 (+5 FPS, README.md:22-30)
+NOISE = [0, 5, 10, 20, 40]                                                  # colour_noise.py:8 (+ clean)
+
+
+def cheek_rects(vhr, spec):
+    from video_heart_rate_b200 import host
+    lm = spec.landmarks()
+    r = host.slice_rects(host.cheek_roi_clamped(host.bbox_clamped(lm[None], spec.W, spec.H), spec.W, spec.H), spec.W, spec.H)[0]
+    return np.tile(r, (spec.T, 1, 1)).astype(np.int32)
+
+
+def run_c1(eng, vhr):
+    """rppg_VIDEO.py signal path on the c1 clip: process_frame trace (overdraw quirk on) -> per-frame
+    sliding-window Butterworth / Cheby2 / FIR + Welch BPM, and the EVM variant; compared with the
+    CPU oracle (the reference's own functions restated)."""
+    import torch
+    from oracle import bpm as obpm, roi as oroi, synth as osynth
+    from video_heart_rate_b200.pipeline import video_trace, video_bpm_series, evm_bpm
+    kw = dict(T=150, H=144, W=256, fps=5.0, pulse_hz=1.2, seed=0)
+    spec, ospec = vhr.SynthSpec(**kw), osynth.SynthParams(**kw)
+    fr = eng.synth_clip(spec)
+    lm = spec.landmarks()
+    t0 = time.perf_counter()
+    green = video_trace(eng, fr, lm, overdraw=True)
+    series = video_bpm_series(eng, green, 5.0)
+    torch.cuda.synchronize()
+    gpu_s = time.perf_counter() - t0
+    frames = osynth.synth_frames(ospec)
+    t0 = time.perf_counter()
+    g_ref = [oroi.process_frame_green(f, lm[:, 0], lm[:, 1]) for f in frames]
+    exp = obpm.video_window_bpm(g_ref, 5.0)
+    cpu_s = time.perf_counter() - t0
+    same_trace = bool(np.array_equal(green.cpu().numpy(), np.asarray(g_ref)))
+    same_bpm = all(series["butter"][j] == e[1] and series["cheby2"][j] == e[2] and (e[3] is None) == bool(np.isnan(series["fir"][j]))
+                   for j, e in enumerate(exp)) and len(exp) == len(series["frame"])
+    evm = evm_bpm(eng, fr, 5.0, cheek_rects(vhr, spec), LEVELS, BAND, ALPHA)
+    return {"config": "c1", "frames": 150, "trace_bit_exact": same_trace, "bpm_identical": bool(same_bpm),
+            "windows": len(exp), "bpm_butter_last": float(series["butter"][-1]), "bpm_cheby2_last": float(series["cheby2"][-1]),
+            "fir": "reference raises (window 50 <= padlen 123)", "evm_bpm": float(evm["bpm"][0]),
+            "gpu_s": gpu_s, "cpu_oracle_s": cpu_s}
+
+
+def run_c2(eng, vhr, steps=5):
+    import torch
+    from video_heart_rate_b200.pipeline import evm_bpm
+    spec = vhr.SynthSpec(T=1800, H=720, W=1280, fps=30.0, pulse_hz=1.2, seed=2)
+    fr = eng.synth_clip(spec)
+    rects = torch.as_tensor(cheek_rects(vhr, spec), device=eng.tdev)
+    out = torch.empty((1800, 720, 1280, 3), dtype=torch.float32, device=eng.tdev)
+    for _ in range(2):
+        r = evm_bpm(eng, fr, 30.0, rects, LEVELS, BAND, ALPHA, out_f32=out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        r = evm_bpm(eng, fr, 30.0, rects, LEVELS, BAND, ALPHA, out_f32=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    bytes_per_frame = 18 * 1280 * 720 + 48 * 80 * 45
+    return {"config": "c2", "frames_per_s": 1800 / (ms / 1e3), "ms_per_clip": ms, "bpm": float(r["bpm"][0]),
+            "expected_bpm": 72.0, "path_gbs": bytes_per_frame * 1800 / (ms / 1e3) / 1e9}
+
+
+def run_c3(eng, vhr):
+    """Sliding window: 60 s stream, 10 s window (300 frames), 1 s hop -> 51 windows.  Latency = time
+    from 'the hop's 30 new frames are on the device' to 'BPM on the host' for the whole window."""
+    import torch
+    from video_heart_rate_b200.pipeline import evm_bpm
+    spec = vhr.SynthSpec(T=1800, H=480, W=640, fps=30.0, pulse_hz=1.4, seed=3)
+    fr = eng.synth_clip(spec)
+    rects_all = torch.as_tensor(cheek_rects(vhr, spec), device=eng.tdev)
+    out = torch.empty((300, 480, 640, 3), dtype=torch.float32, device=eng.tdev)
+    lat, bpms = [], []
+    for w in range(-3, 51):                       # 3 warm-up windows
+        s = max(w, 0) * 30
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = evm_bpm(eng, fr[s:s + 300], 30.0, rects_all[s:s + 300], LEVELS, BAND, ALPHA, out_f32=out)
+        b = float(r["bpm"][0].item())
+        dt = time.perf_counter() - t0
+        if w >= 0:
+            lat.append(dt * 1e3)
+            bpms.append(b)
+    return {"config": "c3", "windows": len(lat), "latency_ms_median": float(np.median(lat)), "latency_ms_p95": float(np.percentile(lat, 95)),
+            "latency_ms_max": float(np.max(lat)), "bpm_unique": sorted(set(round(x, 3) for x in bpms)), "expected_bpm": 84.0}
+
+
+def c5_windows(n=512):
+    """(height, fps, noise_sigma, pulse_hz, seed) grid; truth BPM = 60 * pulse_hz rounded to the window's bin."""
+    pulses = [1.0, 1.33, 1.75, 2.2]           # two on-bin, two off-bin (10 s windows: 0.1 Hz = 6 BPM bins)
+    out = []
+    for ip, f in enumerate(pulses):
+        for h in RES:
+            for fps in FPS:
+                for sg in NOISE:
+                    out.append((h, fps, sg, f, len(out)))
+    return out[:n]
+
+
+def run_c5(eng, vhr, n=512, seconds=10.0):
+    import torch
+    import torch.distributed as dist
+    from video_heart_rate_b200 import parallel
+    from video_heart_rate_b200.pipeline import evm_bpm
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    wins = c5_windows(n)
+    costs = [RES[h] * h * fps * seconds for (h, fps, _, _, _) in wins]
+    mine = parallel.shard_by_cost(costs, world)[rank]
+    local = {}
+    t0 = time.perf_counter()
+    for i in mine:
+        h, fps, sg, f, seed = wins[i]
+        T = int(fps * seconds)
+        spec = vhr.SynthSpec(T=T, H=h, W=RES[h], fps=float(fps), pulse_hz=f, seed=seed, clip=i)
+        fr = eng.synth_clip(spec)
+        if sg > 0:
+            fr = eng.degrade_noise(fr, sg, seed=seed, clip=i, out=fr)      # colour_noise.add_gaussian_noise
+        r = evm_bpm(eng, fr, float(fps), cheek_rects(vhr, spec), LEVELS, BAND, ALPHA, out_f32=False)
+        local[i] = [float(r["bpm"][0].item())]
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    got = parallel.gather_results(local, len(wins), 1, device=eng.tdev)
+    if rank != 0:
+        return None
+    bpm = got[:, 0]
+    truth = np.array([60.0 * f for (_, _, _, f, _) in wins])
+    err = np.abs(bpm - truth)
+    by_noise = {str(sg): float(np.nanmean(err[[j for j, w in enumerate(wins) if w[2] == sg]])) for sg in NOISE}
+    by_res = {str(h): float(np.nanmean(err[[j for j, w in enumerate(wins) if w[0] == h]])) for h in RES}
+    by_fps = {str(fp): float(np.nanmean(err[[j for j, w in enumerate(wins) if w[1] == fp]])) for fp in FPS}
+    frames = sum(int(w[1] * seconds) for w in wins)
+    return {"config": "c5", "windows": len(wins), "n_gpus": world, "mae_bpm": float(np.nanmean(err)), "mae_by_noise": by_noise,
+            "mae_by_height": by_res, "mae_by_fps": by_fps, "nan_windows": int(np.isnan(bpm).sum()),
+            "seconds_rank0": dt, "frames": frames,
+            "note": "bin resolution is 6 BPM at 10 s windows; MAE <= 3 means the peak bin is the nearest bin"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", required=True, choices=["c1", "c2", "c3", "c5"])
+    ap.add_argument("--windows", type=int, default=512)
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    import video_heart_rate_b200 as vhr
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    eng = vhr.Engine(local_rank)
+    res = {"c1": lambda: run_c1(eng, vhr), "c2": lambda: run_c2(eng, vhr), "c3": lambda: run_c3(eng, vhr),
+           "c5": lambda: run_c5(eng, vhr, args.windows)}[args.config]()
+    if res is not None:
+        print(json.dumps(res), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
