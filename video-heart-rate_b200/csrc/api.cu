@@ -76,6 +76,7 @@ int vhr_destroy(vhr_ctx* ctx) {
     if (ctx->tw) cudaFree(ctx->tw);
     if (ctx->mask) cudaFree(ctx->mask);
     if (ctx->hostpath) cudaFree(ctx->hostpath);
+    if (ctx->sep_tab) cudaFree(ctx->sep_tab);
     delete ctx;
     return VHR_OK;
 }

@@ -538,6 +538,11 @@ extern "C" int vhr_collapse_addback_roi(vhr_ctx* ctx, const float* d_level, cons
     VHR_REQUIRE(ctx, K == 0 || (d_rects && d_roi_mean), "ROI pointers missing");
     VHR_REQUIRE(ctx, d_out_f32 || d_out_u8 || K > 0, "nothing to compute");
     cudaStream_t stream = (cudaStream_t)stream_;
+    {
+        const char* impl = getenv("VHR_COLLAPSE_IMPL");
+        if (!impl || strcmp(impl, "tiled") != 0)
+            return vhr_collapse_sep(ctx, d_level, d_frames, T, H, W, levels, d_out_f32, d_out_u8, d_rects, K, d_roi_mean, stream);
+    }
     ColArgs a;
     memset(&a, 0, sizeof(a));
     a.lvl = d_level; a.frames = d_frames; a.out_f32 = d_out_f32; a.out_u8 = d_out_u8;

@@ -26,10 +26,18 @@ struct vhr_ctx {
     // context-owned buffers of the *_host convenience path
     void* hostpath = nullptr;
     size_t hostpath_bytes = 0;
+    // composite pyrUp weight tables of the collapse (collapse_sep.cu), keyed by shape
+    void* sep_tab = nullptr;
+    size_t sep_tab_bytes = 0;
+    long long sep_key = -1;
 };
 
 void vhr_set_error(vhr_ctx* ctx, const char* fmt, ...);
 int vhr_scratch(vhr_ctx* ctx, size_t bytes, void** out);
+// collapse_sep.cu: separable-composite collapse (arguments as vhr_collapse_addback_roi, validated by the caller)
+int vhr_collapse_sep(vhr_ctx* ctx, const float* d_level, const uint8_t* d_frames, int T, int H, int W, int levels,
+                     float* d_out_f32, uint8_t* d_out_u8, const int32_t* d_rects, int K, double* d_roi_mean,
+                     cudaStream_t stream);
 
 #define VHR_CHECK_CUDA(ctx, expr)                                                        \
     do {                                                                                 \
