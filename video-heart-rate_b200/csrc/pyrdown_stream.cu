@@ -1,0 +1,471 @@
+// Streaming fast path of the fused pyrDown cascade (W % 16 == 0, 16-byte aligned frames); the
+// generic kernel in pyrdown.cu covers every other shape with the same arithmetic.
+//
+// Same spec as pyrdown.cu (cv2.pyrDown float32 semantics; levels 1-2 exact integers * 2^-8l).
+// Layout of the work, driven by the ncu captures in profiles/ (the previous fast path spent two
+// thirds of its 4.4e9 warp-instructions on levels >= 2, which hold a quarter of the data, and
+// was issue-bound at 25 % of DRAM peak):
+//   * A thread owns a fixed column group: 8 input pixels -> 4 px of level 1 -> 2 px of level 2
+//     -> 1 px of levels >= 3, and streams rows top to bottom.  Levels 1 AND 2 live entirely in
+//     registers: level 1 = 4 IDP4A per value on the raw bytes + a packed-uint16 vertical pass on
+//     a register window; the finished level-1 row is handed to the level-2 horizontal pass
+//     (3 IDP2A per value) by WARP SHUFFLE (lanes 0 and 31 of each warp are halo lanes that
+//     recompute the neighbour warp's edge column, so warps never exchange level-1 data), and the
+//     level-2 vertical pass runs on a second register window.  Shared memory / block barriers are
+//     touched once per LEVEL-2 row (every 4 input rows), not once per row of every level.
+//   * Input rows arrive by cp.async.bulk (TMA engine, UBLKCP) into a shared-memory ring, one
+//     mbarrier per slot, issued up to a ring ahead by one thread: HBM requests in flight do not
+//     depend on registers or occupancy.  Each input byte is read from HBM once.
+//   * Levels >= 3 (1/16 of the data): horizontal-first with thread-private 5-row H rings in
+//     shared memory, newest finished row per level double-buffered, one barrier per produced row.
+//   * Persistent grid over the flattened (frame, final-row) space, equal contiguous shares.
+#include "common.cuh"
+
+namespace {
+
+constexpr int HR = 5;        // rows in a private H ring (exactly the vertical footprint)
+constexpr int LANES = 30;    // column groups per warp (lanes 1..30); lanes 0 / 31 are halo lanes
+
+struct StreamArgs {
+    const uint8_t* frames;
+    float* out;
+    int T, H, W, levels;
+    int w[VHR_MAX_LEVELS + 1];
+    int h[VHR_MAX_LEVELS + 1];
+    long long total_rows;
+    int nt;                                // column groups = W / 8
+    int nr;                                // rows in the input ring
+    int rowbytes;                          // 3 W
+    int in_off;                            // byte offset of ring row 0 (16 bytes of slack either side of the ring)
+    int ring_off[VHR_MAX_LEVELS + 1];      // levels 2..L-1: newest rows, float planar, double-buffered
+    int ring_stride[VHR_MAX_LEVELS + 1];   // floats per channel plane row
+    int hring_off[VHR_MAX_LEVELS + 1];     // levels 3..L: private H rings
+};
+
+// ---- PTX helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "W_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra W_%=;\n\t}"
+        :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// ---- level-1 horizontal pass: compile-time IDP4A weight words ---------------------------------
+__host__ __device__ constexpr int fdiv4(int b) { return b >= 0 ? b / 4 : -((-b + 3) / 4); }
+__host__ __device__ constexpr uint32_t tap_word(int j0, int wi) {
+    uint32_t r = 0;
+    const int wt[5] = {1, 4, 6, 4, 1};
+    for (int d = 0; d < 5; ++d) {
+        int b = j0 + 3 * (d - 2);
+        int w = fdiv4(b);
+        if (w == wi) r |= (uint32_t)wt[d] << (8 * (b - 4 * w));
+    }
+    return r;
+}
+template <int O, int WI>
+struct Tap {
+    __device__ static __forceinline__ uint32_t run(const uint32_t (&wd)[9], uint32_t acc) {
+        constexpr uint32_t k = tap_word(6 * (O / 3) + (O % 3), WI);
+        if (k != 0) acc = __dp4a(wd[WI + 2], k, acc);
+        return Tap<O, WI + 1>::run(wd, acc);
+    }
+};
+template <int O>
+struct Tap<O, 7> {
+    __device__ static __forceinline__ uint32_t run(const uint32_t (&)[9], uint32_t acc) { return acc; }
+};
+// 12 outputs (pixel m = 0..3, channel c) -> 6 packed registers: hp[2c] = (m0 | m1 << 16),
+// hp[2c+1] = (m2 | m3 << 16)
+template <int C>
+struct HPass {
+    __device__ static __forceinline__ void run(const uint32_t (&wd)[9], uint32_t (&hp)[6]) {
+        const uint32_t o0 = Tap<0 + C, -2>::run(wd, 0u), o1 = Tap<3 + C, -2>::run(wd, 0u);
+        const uint32_t o2 = Tap<6 + C, -2>::run(wd, 0u), o3 = Tap<9 + C, -2>::run(wd, 0u);
+        hp[2 * C] = __byte_perm(o0, o1, 0x5410);
+        hp[2 * C + 1] = __byte_perm(o2, o3, 0x5410);
+        HPass<C + 1>::run(wd, hp);
+    }
+};
+template <>
+struct HPass<3> {
+    __device__ static __forceinline__ void run(const uint32_t (&)[9], uint32_t (&)[6]) {}
+};
+
+template <int L>
+struct Stream {
+    const StreamArgs& a;
+    unsigned char* smem;
+    const int i;              // column group of this lane (-1 / >= nt on idle halo lanes)
+    const bool own;           // lane owns outputs of column group i
+    const bool first_col, last_col;
+    const unsigned char* rd;  // smem + in_off + 24 * clamp(i) - 8
+    uint32_t bar0;            // shared address of mbarrier 0
+    // input ring, consumer side (block-uniform)
+    int c_slot, c_phase, kcons;
+    // producer side (thread 0)
+    int p_slot, issued, k_total, vr0;
+    const uint8_t* frame;
+    float* out_frame;
+    int nextr[VHR_MAX_LEVELS + 1], lastr[VHR_MAX_LEVELS + 1];
+    uint32_t w0[6], w1[6], w2[6];      // level-1 H rows carried between level-1 rows
+    int tapofs[VHR_MAX_LEVELS + 1][5]; // levels >= 3: byte offsets of the horizontal taps in a row of level l-1
+    int hps[VHR_MAX_LEVELS + 1], rps[VHR_MAX_LEVELS + 1];
+
+    __device__ Stream(const StreamArgs& a_, unsigned char* s, int col)
+        : a(a_), smem(s), i(col), own((threadIdx.x & 31) >= 1 && (threadIdx.x & 31) <= LANES && col < a_.nt),
+          first_col(col == 0), last_col(col == a_.nt - 1) {
+        const int ic = min(max(col, 0), a.nt - 1);
+        rd = smem + a.in_off + 24 * ic - 8;
+        bar0 = smem_u32(smem);
+        c_slot = 0; c_phase = 0; kcons = 0; p_slot = 0; issued = 0; k_total = 0; vr0 = 0;
+#pragma unroll
+        for (int l = 2; l <= L; ++l) {
+            hps[l] = a.w[l] * 4;
+            rps[l] = a.ring_stride[l] * 4;
+            if (l >= 3) {
+#pragma unroll
+                for (int d = 0; d < 5; ++d) tapofs[l][d] = 4 * vhr_reflect101(2 * min(ic, a.w[l] - 1) - 2 + d, a.w[l - 1]);
+            }
+        }
+    }
+
+    // ---- input ring -------------------------------------------------------------------------
+    // Block barrier + refill: every row consumed before the barrier has been read by all
+    // threads, so its slot may be overwritten.
+    __device__ __forceinline__ void sync_refill() {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int lim = min(k_total, kcons + a.nr);
+            while (issued < lim) {
+                const int row = vhr_reflect101(vr0 + issued, a.H);
+                const uint32_t bar = bar0 + 8 * p_slot;
+                mbar_expect_tx(bar, (uint32_t)a.rowbytes);
+                bulk_g2s(smem_u32(smem + a.in_off + p_slot * a.rowbytes), frame + (size_t)row * a.rowbytes,
+                         (uint32_t)a.rowbytes, bar);
+                p_slot = (p_slot + 1 == a.nr) ? 0 : p_slot + 1;
+                ++issued;
+            }
+        }
+    }
+    // Next input row of the segment -> its level-1 horizontal pass (6 packed registers).
+    __device__ __forceinline__ void consume(uint32_t (&hp)[6]) {
+        mbar_wait(bar0 + 8 * c_slot, (uint32_t)c_phase);
+        const unsigned char* p = rd + c_slot * a.rowbytes;
+        uint32_t wd[9];
+        const uint2 q0 = *reinterpret_cast<const uint2*>(p), q1 = *reinterpret_cast<const uint2*>(p + 8);
+        const uint2 q2 = *reinterpret_cast<const uint2*>(p + 16), q3 = *reinterpret_cast<const uint2*>(p + 24);
+        wd[8] = *reinterpret_cast<const uint32_t*>(p + 32);
+        wd[0] = q0.x; wd[1] = q0.y; wd[2] = q1.x; wd[3] = q1.y; wd[4] = q2.x; wd[5] = q2.y; wd[6] = q3.x; wd[7] = q3.y;
+        if (first_col) {                                       // pixels -2,-1 reflect to 2,1
+            wd[0] = __byte_perm(wd[3], 0, 0x3244);
+            const uint32_t tt = __byte_perm(wd[2], wd[3], 0x5430);
+            wd[1] = __byte_perm(tt, wd[4], 0x3214);
+        }
+        if (last_col) wd[8] = __byte_perm(wd[6], wd[7], 0x0432);   // pixel W reflects to W-2
+        HPass<0>::run(wd, hp);
+        ++kcons;
+        if (++c_slot == a.nr) { c_slot = 0; c_phase ^= 1; }
+    }
+
+    // ---- level 1: one row = two new input rows + the packed vertical pass ---------------------
+    __device__ __forceinline__ void prime() {       // first three input rows of a segment
+#pragma unroll 1
+        for (int p = 0; p < 3; ++p) {
+            uint32_t hn[6];
+            consume(hn);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { w0[k] = w1[k]; w1[k] = w2[k]; w2[k] = hn[k]; }
+        }
+    }
+    __device__ __forceinline__ void l1_row(uint32_t (&v)[6]) {
+        uint32_t w3[6], w4[6];
+        consume(w3);
+        consume(w4);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {      // packed 16-bit lanes (max 65280: no carry between halves)
+            v[k] = (w0[k] + w4[k]) + ((w1[k] + w3[k]) << 2) + w2[k] * 6u;
+            w0[k] = w2[k]; w1[k] = w3[k]; w2[k] = w4[k];
+        }
+    }
+    // level-2 horizontal pass of a finished level-1 row: neighbours' pixels by shuffle
+    __device__ __forceinline__ void l2_hrow(const uint32_t (&v)[6], uint32_t (&o)[6]) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            uint32_t pv = __shfl_up_sync(0xffffffffu, v[2 * c + 1], 1);     // level-1 px 4i-2, 4i-1
+            uint32_t nv = __shfl_down_sync(0xffffffffu, v[2 * c], 1);       // level-1 px 4i+4
+            if (first_col) pv = __byte_perm(v[2 * c + 1], v[2 * c], 0x7610);   // px -2,-1 <- px 2,1
+            if (last_col) nv = v[2 * c + 1];                                   // px w1 <- px w1-2
+            uint32_t o0 = __dp2a_lo(pv, 0x0401u, 0u);
+            o0 = __dp2a_lo(v[2 * c], 0x0406u, o0);
+            o0 = __dp2a_lo(v[2 * c + 1], 0x0001u, o0);
+            uint32_t o1 = __dp2a_lo(v[2 * c], 0x0401u, 0u);
+            o1 = __dp2a_lo(v[2 * c + 1], 0x0406u, o1);
+            o1 = __dp2a_lo(nv, 0x0001u, o1);
+            o[2 * c] = o0; o[2 * c + 1] = o1;
+        }
+    }
+
+    __device__ __forceinline__ void begin_segment(int t, int r0, int r1) {
+        frame = a.frames + (size_t)t * a.H * a.rowbytes;
+        out_frame = a.out + (size_t)t * a.h[L] * a.w[L] * 3;
+        int f = r0, e = r1 - 1;
+        nextr[L] = f; lastr[L] = e;
+#pragma unroll
+        for (int l = L - 1; l >= 1; --l) {
+            f = max(0, 2 * f - 2);
+            e = min(a.h[l] - 1, 2 * e + 2);
+            nextr[l] = f; lastr[l] = e;
+        }
+        // input rows of the segment: virtual rows 2*first-2 .. 2*last+2 (reflected by the producer)
+        vr0 = 2 * nextr[1] - 2;
+        k_total = 2 * (lastr[1] - nextr[1] + 1) + 3;
+        issued = 0;
+        kcons = 0;
+    }
+
+    // ---- levels >= 3: a finished row `r` of level l-1 sits in its shared ring ------------------
+    template <int l>
+    __device__ __forceinline__ void on_row(int r) {
+        const bool ownl = own && i < a.w[l];
+        unsigned char* const hbase = smem + a.hring_off[l] + (r % HR) * 3 * hps[l];        // H-ring slot of source row r
+        const unsigned char* const rsrc = smem + a.ring_off[l - 1] + (r & 1) * 3 * rps[l - 1];
+        if (ownl) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const unsigned char* p = rsrc + ch * rps[l - 1];
+                const float t0 = *reinterpret_cast<const float*>(p + tapofs[l][0]);
+                const float t1 = *reinterpret_cast<const float*>(p + tapofs[l][1]);
+                const float t2 = *reinterpret_cast<const float*>(p + tapofs[l][2]);
+                const float t3 = *reinterpret_cast<const float*>(p + tapofs[l][3]);
+                const float t4 = *reinterpret_cast<const float*>(p + tapofs[l][4]);
+                *reinterpret_cast<float*>(hbase + ch * hps[l] + 4 * i) = t2 * 6.0f + (t1 + t3) * 4.0f + t0 + t4;
+            }
+        }
+        const int hp = a.h[l - 1];
+        while (nextr[l] <= lastr[l] && min(2 * nextr[l] + 2, hp - 1) <= r) {
+            const int q = nextr[l];
+            int so[5];
+            const int ss = 3 * hps[l];
+#pragma unroll
+            for (int d = 0; d < 5; ++d) so[d] = (vhr_reflect101(2 * q - 2 + d, hp) % HR) * ss;
+            const unsigned char* const hb = smem + a.hring_off[l];
+            if (ownl) {
+                unsigned char* const dst = smem + a.ring_off[l < L ? l : 2] + (q & 1) * 3 * rps[l];
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    const unsigned char* hc = hb + ch * hps[l] + 4 * i;
+                    const float s = *reinterpret_cast<const float*>(hc + so[2]) * 6.0f +
+                                    (*reinterpret_cast<const float*>(hc + so[1]) + *reinterpret_cast<const float*>(hc + so[3])) * 4.0f +
+                                    *reinterpret_cast<const float*>(hc + so[0]) + *reinterpret_cast<const float*>(hc + so[4]);
+                    const float v = s * (1.0f / 256.0f);
+                    if constexpr (l == L) out_frame[((size_t)q * a.w[l] + i) * 3 + ch] = v;
+                    else *reinterpret_cast<float*>(dst + ch * rps[l] + 4 * i) = v;
+                }
+            }
+            nextr[l] = q + 1;
+            if constexpr (l < L) {
+                __syncthreads();                    // row q of level l visible to the neighbours
+                on_row<l + 1>(q);
+            }
+        }
+    }
+
+    // ---- one segment ----------------------------------------------------------------------------
+    __device__ __forceinline__ void run_segment() {
+        sync_refill();
+        prime();
+        sync_refill();
+        if constexpr (L == 1) {
+            int n = 0;
+            for (int r = nextr[1]; r <= lastr[1]; ++r) {
+                uint32_t v[6];
+                l1_row(v);
+                if (own) {
+                    float* o = out_frame + ((size_t)r * a.w[1] + 4 * i) * 3;
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) {
+                        o[ch] = (float)(v[2 * ch] & 0xFFFFu) * (1.0f / 256.0f);
+                        o[3 + ch] = (float)(v[2 * ch] >> 16) * (1.0f / 256.0f);
+                        o[6 + ch] = (float)(v[2 * ch + 1] & 0xFFFFu) * (1.0f / 256.0f);
+                        o[9 + ch] = (float)(v[2 * ch + 1] >> 16) * (1.0f / 256.0f);
+                    }
+                }
+                if (++n == 2) { n = 0; sync_refill(); }
+            }
+        } else {
+            const int h1 = a.h[1];
+            const int qf = nextr[2], ql = lastr[2];
+            uint32_t x0[6], x1[6], x2[6];
+            // level-2 H rows 2qf-2 .. 2qf (just row 0 at the top of a frame)
+            const int npro = qf > 0 ? 3 : 1;
+#pragma unroll 1
+            for (int p = 0; p < npro; ++p) {
+                uint32_t v[6], o[6];
+                l1_row(v);
+                l2_hrow(v, o);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) { x0[k] = x1[k]; x1[k] = x2[k]; x2[k] = o[k]; }
+                sync_refill();
+            }
+#pragma unroll 1
+            for (int q = qf; q <= ql; ++q) {
+                uint32_t x3[6], x4[6];
+                const bool has1 = 2 * q + 1 <= h1 - 1, has2 = 2 * q + 2 <= h1 - 1;
+                if (has1) {
+                    uint32_t v[6];
+                    l1_row(v);
+                    l2_hrow(v, x3);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) x3[k] = x1[k];          // row h1 reflects to h1-2 = 2q-1
+                }
+                if (has2) {
+                    uint32_t v[6];
+                    l1_row(v);
+                    l2_hrow(v, x4);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) x4[k] = has1 ? x2[k] : x0[k];   // row 2q+2 reflects to 2q / 2q-2
+                }
+                if (q == 0) {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) { x0[k] = x4[k]; x1[k] = x3[k]; }   // rows -2,-1 reflect to 2,1
+                }
+                float f[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    const uint32_t s = (x0[k] + x4[k]) + 4u * (x1[k] + x3[k]) + 6u * x2[k];     // < 2^24: exact
+                    f[k] = (float)s * (1.0f / 65536.0f);
+                    x0[k] = x2[k]; x1[k] = x3[k]; x2[k] = x4[k];
+                }
+                if (own) {
+                    if constexpr (L == 2) {
+                        float2* o = reinterpret_cast<float2*>(out_frame + ((size_t)q * a.w[2] + 2 * i) * 3);
+                        o[0] = make_float2(f[0], f[2]);      // px 2i: c0 c1
+                        o[1] = make_float2(f[4], f[1]);      //        c2 | px 2i+1: c0
+                        o[2] = make_float2(f[3], f[5]);      //        c1 c2
+                    } else {
+                        unsigned char* const dst = smem + a.ring_off[2] + (q & 1) * 3 * rps[2] + 8 * i;
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch)
+                            *reinterpret_cast<float2*>(dst + ch * rps[2]) = make_float2(f[2 * ch], f[2 * ch + 1]);
+                    }
+                }
+                nextr[2] = q + 1;
+                sync_refill();                      // ring slots recycled; row q of level 2 visible
+                if constexpr (L >= 3) on_row<3>(q);
+            }
+        }
+    }
+};
+
+template <int L, int MAXT>
+__global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) pyrdown_stream_kernel(const StreamArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const long long lo = a.total_rows * blockIdx.x / gridDim.x;
+    const long long hi = a.total_rows * (blockIdx.x + 1) / gridDim.x;
+    if (lo >= hi) return;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.nr; ++s) mbar_init(smem_u32(smem) + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const int col = (int)(threadIdx.x >> 5) * LANES + (int)(threadIdx.x & 31) - 1;
+    Stream<L> st(a, smem, col);
+    const int hL = a.h[L];
+    long long pos = lo;
+    while (pos < hi) {
+        const int t = (int)(pos / hL);
+        const int r0 = (int)(pos - (long long)t * hL);
+        const long long frame_end = (long long)(t + 1) * hL;
+        const int r1 = (int)((hi < frame_end ? hi : frame_end) - (long long)t * hL);
+        st.begin_segment(t, r0, r1);
+        st.run_segment();               // starts with a block barrier: the previous segment's shared rows are dead
+        pos += r1 - r0;
+    }
+}
+
+template <int L, int MAXT>
+int launch_stream(vhr_ctx* ctx, const StreamArgs& a, int threads, int smem_bytes, cudaStream_t stream) {
+    auto kern = pyrdown_stream_kernel<L, MAXT>;
+    VHR_CHECK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    int per_sm = 0;
+    VHR_CHECK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem_bytes));
+    if (per_sm < 1) return VHR_ERR_UNSUPPORTED;
+    long long grid = (long long)per_sm * ctx->num_sms;
+    if (grid > a.total_rows) grid = a.total_rows;
+    kern<<<(int)grid, threads, smem_bytes, stream>>>(a);
+    return vhr_after_launch(ctx, "pyrdown_stream_kernel");
+}
+
+template <int MAXT>
+int dispatch_stream(vhr_ctx* ctx, const StreamArgs& a, int threads, int smem_bytes, cudaStream_t stream) {
+    switch (a.levels) {
+        case 1: return launch_stream<1, MAXT>(ctx, a, threads, smem_bytes, stream);
+        case 2: return launch_stream<2, MAXT>(ctx, a, threads, smem_bytes, stream);
+        case 3: return launch_stream<3, MAXT>(ctx, a, threads, smem_bytes, stream);
+        case 4: return launch_stream<4, MAXT>(ctx, a, threads, smem_bytes, stream);
+        case 5: return launch_stream<5, MAXT>(ctx, a, threads, smem_bytes, stream);
+        case 6: return launch_stream<6, MAXT>(ctx, a, threads, smem_bytes, stream);
+    }
+    return VHR_ERR_INVALID;
+}
+
+}  // namespace
+
+// Returns VHR_ERR_UNSUPPORTED (without setting an error) when the shape is not eligible.
+int vhr_pyrdown_stream(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int W, int levels, float* d_level,
+                       cudaStream_t stream) {
+    if (W % 16 != 0 || W > 8 * LANES * 16 || (reinterpret_cast<uintptr_t>(d_frames) & 15) != 0 ||
+        (reinterpret_cast<uintptr_t>(d_level) & 7) != 0)
+        return VHR_ERR_UNSUPPORTED;
+    StreamArgs a;
+    memset(&a, 0, sizeof(a));
+    a.frames = d_frames; a.out = d_level; a.T = T; a.H = H; a.W = W; a.levels = levels;
+    PyrDims d = vhr_make_dims(W, H, levels);
+    for (int l = 0; l <= VHR_MAX_LEVELS; ++l) { a.w[l] = d.w[l]; a.h[l] = d.h[l]; }
+    if (a.h[levels - 1] < 2) return VHR_ERR_UNSUPPORTED;           // the register windows assume >= 2 source rows
+    a.total_rows = (long long)T * a.h[levels];
+    a.nt = W / 8;
+    a.rowbytes = 3 * W;
+    const int warps = (a.nt + LANES - 1) / LANES;
+    const int threads = warps * 32;
+    auto al16 = [](int v) { return (v + 15) & ~15; };
+    int fixed = 0;                                                  // everything but the input ring
+    for (int l = 2; l < levels; ++l) {
+        a.ring_stride[l] = (a.w[l] + 3) & ~3;
+        fixed = al16(fixed + 2 * 3 * a.ring_stride[l] * 4);
+    }
+    for (int l = 3; l <= levels; ++l) fixed = al16(fixed + HR * 3 * a.w[l] * 4);
+    // input ring depth: as deep as two CTAs per SM allow (12 rows = 8..12 rows of HBM requests in flight per CTA)
+    const int budget = (threads <= 256 ? ctx->smem_optin / 2 - 2048 : ctx->smem_optin - 1024);
+    int nr = 12;
+    while (nr > 4 && al16(8 * nr) + 32 + nr * a.rowbytes + fixed > budget) --nr;
+    if (al16(8 * nr) + 32 + nr * a.rowbytes + fixed > ctx->smem_optin) return VHR_ERR_UNSUPPORTED;
+    a.nr = nr;
+    int off = al16(8 * nr);
+    a.in_off = off + 16;
+    off = al16(a.in_off + nr * a.rowbytes + 16);
+    for (int l = 2; l < levels; ++l) {
+        a.ring_off[l] = off;
+        off = al16(off + 2 * 3 * a.ring_stride[l] * 4);
+    }
+    for (int l = 3; l <= levels; ++l) {
+        a.hring_off[l] = off;
+        off = al16(off + HR * 3 * a.w[l] * 4);
+    }
+    if (threads <= 256) return dispatch_stream<256>(ctx, a, threads, off, stream);
+    return dispatch_stream<512>(ctx, a, threads, off, stream);
+}
