@@ -112,16 +112,20 @@ struct Stream {
     const bool own;           // lane owns outputs of column group i
     const bool first_col, last_col;
     const unsigned char* rd;  // smem + in_off + 24 * clamp(i) - 8
-    uint32_t bar0;            // shared address of mbarrier 0
+    uint32_t bar0;            // shared address of mbarrier 0 (input ring: nr barriers; then the row barrier)
     // input ring, consumer side (block-uniform)
     int c_slot, c_phase, kcons;
     // producer side (thread 0)
     int p_slot, issued, k_total, vr0;
+    // deferred row barrier: level-2 row `pend` has been written and signalled, its consumers
+    // (levels >= 3) run one level-1 row later so that nobody waits for stragglers
+    int pend, rb_phase, kc_arr;
     const uint8_t* frame;
     float* out_frame;
     int nextr[VHR_MAX_LEVELS + 1], lastr[VHR_MAX_LEVELS + 1];
+    int hslot[VHR_MAX_LEVELS + 1];     // levels >= 3: H-ring slot of the newest source row
     uint32_t w0[6], w1[6], w2[6];      // level-1 H rows carried between level-1 rows
-    int tapofs[VHR_MAX_LEVELS + 1][5]; // levels >= 3: byte offsets of the horizontal taps in a row of level l-1
+    uint32_t apron;                    // bit 4(l-2)+k: this lane's pixel also fills apron cell k of ring l
     int hps[VHR_MAX_LEVELS + 1], rps[VHR_MAX_LEVELS + 1];
 
     __device__ Stream(const StreamArgs& a_, unsigned char* s, int col)
@@ -131,24 +135,29 @@ struct Stream {
         rd = smem + a.in_off + 24 * ic - 8;
         bar0 = smem_u32(smem);
         c_slot = 0; c_phase = 0; kcons = 0; p_slot = 0; issued = 0; k_total = 0; vr0 = 0;
+        pend = -1; rb_phase = 0; kc_arr = 0;
+        apron = 0;
 #pragma unroll
         for (int l = 2; l <= L; ++l) {
             hps[l] = a.w[l] * 4;
             rps[l] = a.ring_stride[l] * 4;
-            if (l >= 3) {
-#pragma unroll
-                for (int d = 0; d < 5; ++d) tapofs[l][d] = 4 * vhr_reflect101(2 * min(ic, a.w[l] - 1) - 2 + d, a.w[l - 1]);
+            hslot[l] = 0;
+            if (l >= 3 && l < L && own && col < a.w[l]) {
+                // apron cells of ring l: positions -2, -1, w, w+1 hold the reflect-101 neighbours
+                const int w = a.w[l];
+                if (vhr_reflect101(-2, w) == col) apron |= 1u << (4 * (l - 2));
+                if (vhr_reflect101(-1, w) == col) apron |= 2u << (4 * (l - 2));
+                if (vhr_reflect101(w, w) == col) apron |= 4u << (4 * (l - 2));
+                if (vhr_reflect101(w + 1, w) == col) apron |= 8u << (4 * (l - 2));
             }
         }
     }
 
     // ---- input ring -------------------------------------------------------------------------
-    // Block barrier + refill: every row consumed before the barrier has been read by all
-    // threads, so its slot may be overwritten.
-    __device__ __forceinline__ void sync_refill() {
-        __syncthreads();
+    // Rows [0, done) of the segment have been read by every thread: their slots may be refilled.
+    __device__ __forceinline__ void refill(int done) {
         if (threadIdx.x == 0) {
-            const int lim = min(k_total, kcons + a.nr);
+            const int lim = min(k_total, done + a.nr);
             while (issued < lim) {
                 const int row = vhr_reflect101(vr0 + issued, a.H);
                 const uint32_t bar = bar0 + 8 * p_slot;
@@ -159,6 +168,10 @@ struct Stream {
                 ++issued;
             }
         }
+    }
+    __device__ __forceinline__ void sync_refill() {
+        __syncthreads();
+        refill(kcons);
     }
     // Next input row of the segment -> its level-1 horizontal pass (6 packed registers).
     __device__ __forceinline__ void consume(uint32_t (&hp)[6]) {
@@ -217,6 +230,11 @@ struct Stream {
             o[2 * c] = o0; o[2 * c + 1] = o1;
         }
     }
+    __device__ __forceinline__ void l12_row(uint32_t (&o)[6]) {
+        uint32_t v[6];
+        l1_row(v);
+        l2_hrow(v, o);
+    }
 
     __device__ __forceinline__ void begin_segment(int t, int r0, int r1) {
         frame = a.frames + (size_t)t * a.H * a.rowbytes;
@@ -234,45 +252,70 @@ struct Stream {
         k_total = 2 * (lastr[1] - nextr[1] + 1) + 3;
         issued = 0;
         kcons = 0;
+        pend = -1;
     }
 
     // ---- levels >= 3: a finished row `r` of level l-1 sits in its shared ring ------------------
+    // ring row layout (float, per channel plane): [px -2, -1 | px 0 .. w-1 | px w, w+1]
     template <int l>
     __device__ __forceinline__ void on_row(int r) {
         const bool ownl = own && i < a.w[l];
-        unsigned char* const hbase = smem + a.hring_off[l] + (r % HR) * 3 * hps[l];        // H-ring slot of source row r
-        const unsigned char* const rsrc = smem + a.ring_off[l - 1] + (r & 1) * 3 * rps[l - 1];
+        const int hs = (hslot[l] == HR - 1) ? 0 : hslot[l] + 1;       // slot of source row r (rows arrive in order)
+        hslot[l] = hs;
+        const int ss = 3 * hps[l];
+        unsigned char* const hmine = smem + a.hring_off[l] + 4 * i;
         if (ownl) {
+            const unsigned char* p = smem + a.ring_off[l - 1] + (r & 1) * 3 * rps[l - 1] + 8 * i;   // px 2i-2
+            unsigned char* hdst = hmine + hs * ss;
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
-                const unsigned char* p = rsrc + ch * rps[l - 1];
-                const float t0 = *reinterpret_cast<const float*>(p + tapofs[l][0]);
-                const float t1 = *reinterpret_cast<const float*>(p + tapofs[l][1]);
-                const float t2 = *reinterpret_cast<const float*>(p + tapofs[l][2]);
-                const float t3 = *reinterpret_cast<const float*>(p + tapofs[l][3]);
-                const float t4 = *reinterpret_cast<const float*>(p + tapofs[l][4]);
-                *reinterpret_cast<float*>(hbase + ch * hps[l] + 4 * i) = t2 * 6.0f + (t1 + t3) * 4.0f + t0 + t4;
+                const float2 ta = *reinterpret_cast<const float2*>(p);
+                const float2 tb = *reinterpret_cast<const float2*>(p + 8);
+                const float tc = *reinterpret_cast<const float*>(p + 16);
+                *reinterpret_cast<float*>(hdst) = tb.x * 6.0f + (ta.y + tb.y) * 4.0f + ta.x + tc;
+                p += rps[l - 1];
+                hdst += hps[l];
             }
         }
         const int hp = a.h[l - 1];
         while (nextr[l] <= lastr[l] && min(2 * nextr[l] + 2, hp - 1) <= r) {
             const int q = nextr[l];
+            // H-ring slots of the five source rows: row r' sits (r - r') slots behind the newest
             int so[5];
-            const int ss = 3 * hps[l];
 #pragma unroll
-            for (int d = 0; d < 5; ++d) so[d] = (vhr_reflect101(2 * q - 2 + d, hp) % HR) * ss;
-            const unsigned char* const hb = smem + a.hring_off[l];
+            for (int d = 0; d < 5; ++d) {
+                int sl = hs - (r - vhr_reflect101(2 * q - 2 + d, hp));
+                if (sl < 0) sl += HR;
+                so[d] = sl * ss;
+            }
             if (ownl) {
-                unsigned char* const dst = smem + a.ring_off[l < L ? l : 2] + (q & 1) * 3 * rps[l];
+                float v[3];
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {
-                    const unsigned char* hc = hb + ch * hps[l] + 4 * i;
-                    const float s = *reinterpret_cast<const float*>(hc + so[2]) * 6.0f +
-                                    (*reinterpret_cast<const float*>(hc + so[1]) + *reinterpret_cast<const float*>(hc + so[3])) * 4.0f +
-                                    *reinterpret_cast<const float*>(hc + so[0]) + *reinterpret_cast<const float*>(hc + so[4]);
-                    const float v = s * (1.0f / 256.0f);
-                    if constexpr (l == L) out_frame[((size_t)q * a.w[l] + i) * 3 + ch] = v;
-                    else *reinterpret_cast<float*>(dst + ch * rps[l] + 4 * i) = v;
+                    const unsigned char* hc = hmine + ch * hps[l];
+                    const float sum = *reinterpret_cast<const float*>(hc + so[2]) * 6.0f +
+                                      (*reinterpret_cast<const float*>(hc + so[1]) + *reinterpret_cast<const float*>(hc + so[3])) * 4.0f +
+                                      *reinterpret_cast<const float*>(hc + so[0]) + *reinterpret_cast<const float*>(hc + so[4]);
+                    v[ch] = sum * (1.0f / 256.0f);
+                }
+                if constexpr (l == L) {
+                    float* o = out_frame + ((size_t)q * a.w[l] + i) * 3;
+                    o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
+                } else {
+                    unsigned char* const dst = smem + a.ring_off[l] + (q & 1) * 3 * rps[l];
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) *reinterpret_cast<float*>(dst + ch * rps[l] + 8 + 4 * i) = v[ch];
+                    const uint32_t am = (apron >> (4 * (l - 2))) & 15u;
+                    if (am) {
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) {
+                            float* pl = reinterpret_cast<float*>(dst + ch * rps[l]);
+                            if (am & 1u) pl[0] = v[ch];
+                            if (am & 2u) pl[1] = v[ch];
+                            if (am & 4u) pl[2 + a.w[l]] = v[ch];
+                            if (am & 8u) pl[3 + a.w[l]] = v[ch];
+                        }
+                    }
                 }
             }
             nextr[l] = q + 1;
@@ -281,6 +324,56 @@ struct Stream {
                 on_row<l + 1>(q);
             }
         }
+    }
+
+    // ---- level 2: vertical pass + hand-over --------------------------------------------------
+    __device__ __forceinline__ void l2_vpass(const uint32_t (&xa)[6], const uint32_t (&xb)[6], const uint32_t (&xc)[6],
+                                             const uint32_t (&xd)[6], const uint32_t (&xe)[6], float (&f)[6]) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const uint32_t s = (xa[k] + xe[k]) + 4u * (xb[k] + xd[k]) + 6u * xc[k];     // < 2^24: exact
+            f[k] = (float)s * (1.0f / 65536.0f);
+        }
+    }
+    // The row barrier of level-2 row `pend`: every warp has signalled it -> its consumers run now,
+    // and the input rows read before that signal may be recycled.
+    __device__ __forceinline__ void drain() {
+        if (pend < 0) return;
+        mbar_wait(bar0 + 8 * a.nr, (uint32_t)rb_phase);
+        rb_phase ^= 1;
+        refill(kc_arr);
+        if constexpr (L >= 3) on_row<3>(pend);
+        pend = -1;
+    }
+    __device__ __forceinline__ void publish(int q, const float (&f)[6]) {
+        drain();
+        if (own) {
+            if constexpr (L == 2) {
+                float2* o = reinterpret_cast<float2*>(out_frame + ((size_t)q * a.w[2] + 2 * i) * 3);
+                o[0] = make_float2(f[0], f[2]);      // px 2i: c0 c1
+                o[1] = make_float2(f[4], f[1]);      //        c2 | px 2i+1: c0
+                o[2] = make_float2(f[3], f[5]);      //        c1 c2
+            } else {
+                unsigned char* const dst = smem + a.ring_off[2] + (q & 1) * 3 * rps[2];
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch)
+                    *reinterpret_cast<float2*>(dst + ch * rps[2] + 8 + 8 * i) = make_float2(f[2 * ch], f[2 * ch + 1]);
+                if (i <= 1 || last_col) {            // aprons: px -2 <- px 2, px -1 <- px 1, px w2 <- px w2-2
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) {
+                        float* pl = reinterpret_cast<float*>(dst + ch * rps[2]);
+                        if (i == 1) pl[0] = f[2 * ch];
+                        if (i == 0) pl[1] = f[2 * ch + 1];
+                        if (last_col) pl[2 + a.w[2]] = f[2 * ch];
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar0 + 8 * a.nr) : "memory");
+        kc_arr = kcons;
+        pend = q;
+        nextr[2] = q + 1;
     }
 
     // ---- one segment ----------------------------------------------------------------------------
@@ -307,67 +400,48 @@ struct Stream {
             }
         } else {
             const int h1 = a.h[1];
-            const int qf = nextr[2], ql = lastr[2];
+            int q = nextr[2];
+            const int ql = lastr[2];
             uint32_t x0[6], x1[6], x2[6];
-            // level-2 H rows 2qf-2 .. 2qf (just row 0 at the top of a frame)
-            const int npro = qf > 0 ? 3 : 1;
+            // level-2 H rows of level-1 rows 2q-2 .. 2q (rows 0 .. 2 at the top of a frame)
 #pragma unroll 1
-            for (int p = 0; p < npro; ++p) {
-                uint32_t v[6], o[6];
-                l1_row(v);
-                l2_hrow(v, o);
+            for (int p = 0; p < 3; ++p) {
+                uint32_t o[6];
+                l12_row(o);
 #pragma unroll
                 for (int k = 0; k < 6; ++k) { x0[k] = x1[k]; x1[k] = x2[k]; x2[k] = o[k]; }
                 sync_refill();
             }
+            if (q == 0) {                            // rows -2,-1 reflect to 2,1
+                float f[6];
+                l2_vpass(x2, x1, x0, x1, x2, f);
+                publish(0, f);
+                q = 1;
+            }
 #pragma unroll 1
-            for (int q = qf; q <= ql; ++q) {
+            for (; q <= ql; ++q) {
                 uint32_t x3[6], x4[6];
                 const bool has1 = 2 * q + 1 <= h1 - 1, has2 = 2 * q + 2 <= h1 - 1;
                 if (has1) {
-                    uint32_t v[6];
-                    l1_row(v);
-                    l2_hrow(v, x3);
+                    l12_row(x3);
                 } else {
 #pragma unroll
                     for (int k = 0; k < 6; ++k) x3[k] = x1[k];          // row h1 reflects to h1-2 = 2q-1
                 }
+                drain();                                               // consumers of level-2 row q-1
                 if (has2) {
-                    uint32_t v[6];
-                    l1_row(v);
-                    l2_hrow(v, x4);
+                    l12_row(x4);
                 } else {
 #pragma unroll
                     for (int k = 0; k < 6; ++k) x4[k] = has1 ? x2[k] : x0[k];   // row 2q+2 reflects to 2q / 2q-2
                 }
-                if (q == 0) {
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) { x0[k] = x4[k]; x1[k] = x3[k]; }   // rows -2,-1 reflect to 2,1
-                }
                 float f[6];
+                l2_vpass(x0, x1, x2, x3, x4, f);
 #pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    const uint32_t s = (x0[k] + x4[k]) + 4u * (x1[k] + x3[k]) + 6u * x2[k];     // < 2^24: exact
-                    f[k] = (float)s * (1.0f / 65536.0f);
-                    x0[k] = x2[k]; x1[k] = x3[k]; x2[k] = x4[k];
-                }
-                if (own) {
-                    if constexpr (L == 2) {
-                        float2* o = reinterpret_cast<float2*>(out_frame + ((size_t)q * a.w[2] + 2 * i) * 3);
-                        o[0] = make_float2(f[0], f[2]);      // px 2i: c0 c1
-                        o[1] = make_float2(f[4], f[1]);      //        c2 | px 2i+1: c0
-                        o[2] = make_float2(f[3], f[5]);      //        c1 c2
-                    } else {
-                        unsigned char* const dst = smem + a.ring_off[2] + (q & 1) * 3 * rps[2] + 8 * i;
-#pragma unroll
-                        for (int ch = 0; ch < 3; ++ch)
-                            *reinterpret_cast<float2*>(dst + ch * rps[2]) = make_float2(f[2 * ch], f[2 * ch + 1]);
-                    }
-                }
-                nextr[2] = q + 1;
-                sync_refill();                      // ring slots recycled; row q of level 2 visible
-                if constexpr (L >= 3) on_row<3>(q);
+                for (int k = 0; k < 6; ++k) { x0[k] = x2[k]; x1[k] = x3[k]; x2[k] = x4[k]; }
+                publish(q, f);
             }
+            drain();
         }
     }
 };
@@ -380,6 +454,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) pyrdown_stream_kern
     if (lo >= hi) return;
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.nr; ++s) mbar_init(smem_u32(smem) + 8 * s, 1);
+        mbar_init(smem_u32(smem) + 8 * a.nr, blockDim.x >> 5);         // row barrier: one arrival per warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     const int col = (int)(threadIdx.x >> 5) * LANES + (int)(threadIdx.x & 31) - 1;
@@ -436,7 +511,7 @@ int vhr_pyrdown_stream(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int 
     a.frames = d_frames; a.out = d_level; a.T = T; a.H = H; a.W = W; a.levels = levels;
     PyrDims d = vhr_make_dims(W, H, levels);
     for (int l = 0; l <= VHR_MAX_LEVELS; ++l) { a.w[l] = d.w[l]; a.h[l] = d.h[l]; }
-    if (a.h[levels - 1] < 2) return VHR_ERR_UNSUPPORTED;           // the register windows assume >= 2 source rows
+    if (levels == 1 ? H < 2 : a.h[1] < 3) return VHR_ERR_UNSUPPORTED;   // the register windows assume >= 3 level-1 rows
     a.total_rows = (long long)T * a.h[levels];
     a.nt = W / 8;
     a.rowbytes = 3 * W;
@@ -445,17 +520,18 @@ int vhr_pyrdown_stream(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int 
     auto al16 = [](int v) { return (v + 15) & ~15; };
     int fixed = 0;                                                  // everything but the input ring
     for (int l = 2; l < levels; ++l) {
-        a.ring_stride[l] = (a.w[l] + 3) & ~3;
+        a.ring_stride[l] = (a.w[l] + 4 + 3) & ~3;                   // 2 + 2 apron cells
         fixed = al16(fixed + 2 * 3 * a.ring_stride[l] * 4);
     }
     for (int l = 3; l <= levels; ++l) fixed = al16(fixed + HR * 3 * a.w[l] * 4);
     // input ring depth: as deep as two CTAs per SM allow (12 rows = 8..12 rows of HBM requests in flight per CTA)
     const int budget = (threads <= 256 ? ctx->smem_optin / 2 - 2048 : ctx->smem_optin - 1024);
+    // (the deferred row barrier needs >= 7 rows: up to 6 are consumed between two refills)
     int nr = 12;
-    while (nr > 4 && al16(8 * nr) + 32 + nr * a.rowbytes + fixed > budget) --nr;
-    if (al16(8 * nr) + 32 + nr * a.rowbytes + fixed > ctx->smem_optin) return VHR_ERR_UNSUPPORTED;
+    while (nr > 7 && al16(8 * (nr + 1)) + 32 + nr * a.rowbytes + fixed > budget) --nr;
+    if (al16(8 * (nr + 1)) + 32 + nr * a.rowbytes + fixed > ctx->smem_optin) return VHR_ERR_UNSUPPORTED;
     a.nr = nr;
-    int off = al16(8 * nr);
+    int off = al16(8 * (nr + 1));
     a.in_off = off + 16;
     off = al16(a.in_off + nr * a.rowbytes + 16);
     for (int l = 2; l < levels; ++l) {
