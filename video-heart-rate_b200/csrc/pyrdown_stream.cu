@@ -39,7 +39,8 @@ struct StreamArgs {
     int in_off;                            // byte offset of ring row 0 (16 bytes of slack either side of the ring)
     int ring_off[VHR_MAX_LEVELS + 1];      // levels 2..L-1: newest rows, float planar, double-buffered
     int ring_stride[VHR_MAX_LEVELS + 1];   // floats per channel plane row
-    int hring_off[VHR_MAX_LEVELS + 1];     // levels 3..L: private H rings
+    int hring_off[VHR_MAX_LEVELS + 1];     // levels 3..L: H rings (HR rows x 3 planes x w[l])
+    int duty_off;                          // DutyState
 };
 
 // ---- PTX helpers ---------------------------------------------------------------------------
@@ -50,14 +51,27 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n"
-        "W_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@!p bra W_%=;\n\t}"
-        :: "r"(bar), "r"(parity) : "memory");
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
 }
+#ifdef VHR_WATCHDOG
+__device__ __noinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    for (long long spin = 0; !mbar_try_wait(bar, parity); ++spin) {
+        if (spin > 2000000) {
+            if ((threadIdx.x & 31) == 0)
+                printf("WATCHDOG block %d warp %d bar_off %u parity %u\n", blockIdx.x, threadIdx.x >> 5, bar & 0xffffu, parity);
+            __trap();
+        }
+    }
+}
+#else
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+#endif
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -104,6 +118,27 @@ struct HPass<3> {
     __device__ static __forceinline__ void run(const uint32_t (&)[9], uint32_t (&)[6]) {}
 };
 
+// vector loads / stores of C consecutive floats (C = 4, 2, 1), naturally aligned
+template <int C>
+__device__ __forceinline__ void ldv(const float* p, float* x) {
+    if constexpr (C == 4) { const float4 v = *reinterpret_cast<const float4*>(p); x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w; }
+    else if constexpr (C == 2) { const float2 v = *reinterpret_cast<const float2*>(p); x[0] = v.x; x[1] = v.y; }
+    else x[0] = *p;
+}
+template <int C>
+__device__ __forceinline__ void stv(float* p, const float* x) {
+    if constexpr (C == 4) *reinterpret_cast<float4*>(p) = make_float4(x[0], x[1], x[2], x[3]);
+    else if constexpr (C == 2) *reinterpret_cast<float2*>(p) = make_float2(x[0], x[1]);
+    else *p = x[0];
+}
+
+// Block-shared state of the levels >= 3 (they are processed by one warp at a time, in turn).
+struct DutyState {
+    int nextr[VHR_MAX_LEVELS + 1];
+    int lastr[VHR_MAX_LEVELS + 1];
+    int hslot[VHR_MAX_LEVELS + 1];
+};
+
 template <int L>
 struct Stream {
     const StreamArgs& a;
@@ -117,16 +152,16 @@ struct Stream {
     int c_slot, c_phase, kcons;
     // producer side (thread 0)
     int p_slot, issued, k_total, vr0;
-    // deferred row barrier: level-2 row `pend` has been written and signalled, its consumers
-    // (levels >= 3) run one level-1 row later so that nobody waits for stragglers
-    int pend, rb_phase, kc_arr;
+    // rows of level 2 are numbered across segments (dn = rows published so far, the same in every
+    // warp).  Row barrier: phase n completes when every warp has written its part of row n.
+    // Duty barriers (two, alternating): phase n >> 1 of barrier n & 1 completes when the upper
+    // levels have consumed row n.
+    int dn, pend_q, pend_n, kc_arr;
     const uint8_t* frame;
     float* out_frame;
-    int nextr[VHR_MAX_LEVELS + 1], lastr[VHR_MAX_LEVELS + 1];
-    int hslot[VHR_MAX_LEVELS + 1];     // levels >= 3: H-ring slot of the newest source row
+    int nextr[3], lastr[3];            // levels 1, 2 (levels >= 3: DutyState)
+    int seg_next[VHR_MAX_LEVELS + 1], seg_last[VHR_MAX_LEVELS + 1];
     uint32_t w0[6], w1[6], w2[6];      // level-1 H rows carried between level-1 rows
-    uint32_t apron;                    // bit 4(l-2)+k: this lane's pixel also fills apron cell k of ring l
-    int hps[VHR_MAX_LEVELS + 1], rps[VHR_MAX_LEVELS + 1];
 
     __device__ Stream(const StreamArgs& a_, unsigned char* s, int col)
         : a(a_), smem(s), i(col), own((threadIdx.x & 31) >= 1 && (threadIdx.x & 31) <= LANES && col < a_.nt),
@@ -135,23 +170,11 @@ struct Stream {
         rd = smem + a.in_off + 24 * ic - 8;
         bar0 = smem_u32(smem);
         c_slot = 0; c_phase = 0; kcons = 0; p_slot = 0; issued = 0; k_total = 0; vr0 = 0;
-        pend = -1; rb_phase = 0; kc_arr = 0;
-        apron = 0;
-#pragma unroll
-        for (int l = 2; l <= L; ++l) {
-            hps[l] = a.w[l] * 4;
-            rps[l] = a.ring_stride[l] * 4;
-            hslot[l] = 0;
-            if (l >= 3 && l < L && own && col < a.w[l]) {
-                // apron cells of ring l: positions -2, -1, w, w+1 hold the reflect-101 neighbours
-                const int w = a.w[l];
-                if (vhr_reflect101(-2, w) == col) apron |= 1u << (4 * (l - 2));
-                if (vhr_reflect101(-1, w) == col) apron |= 2u << (4 * (l - 2));
-                if (vhr_reflect101(w, w) == col) apron |= 4u << (4 * (l - 2));
-                if (vhr_reflect101(w + 1, w) == col) apron |= 8u << (4 * (l - 2));
-            }
-        }
+        dn = 0; pend_q = -1; pend_n = -1; kc_arr = 0;
     }
+    __device__ __forceinline__ void wait_row(int n) { mbar_wait(bar0 + 8 * a.nr, (uint32_t)(n & 1)); }
+    __device__ __forceinline__ void wait_duty(int n) { mbar_wait(bar0 + 8 * (a.nr + 1 + (n & 1)), (uint32_t)((n >> 1) & 1)); }
+    __device__ __forceinline__ DutyState* duty_state() const { return reinterpret_cast<DutyState*>(smem + a.duty_off); }
 
     // ---- input ring -------------------------------------------------------------------------
     // Rows [0, done) of the segment have been read by every thread: their slots may be refilled.
@@ -240,90 +263,116 @@ struct Stream {
         frame = a.frames + (size_t)t * a.H * a.rowbytes;
         out_frame = a.out + (size_t)t * a.h[L] * a.w[L] * 3;
         int f = r0, e = r1 - 1;
-        nextr[L] = f; lastr[L] = e;
+        seg_next[L] = f; seg_last[L] = e;
 #pragma unroll
         for (int l = L - 1; l >= 1; --l) {
             f = max(0, 2 * f - 2);
             e = min(a.h[l] - 1, 2 * e + 2);
-            nextr[l] = f; lastr[l] = e;
+            seg_next[l] = f; seg_last[l] = e;
         }
+        nextr[1] = seg_next[1]; lastr[1] = seg_last[1];
+        if constexpr (L >= 2) { nextr[2] = seg_next[2]; lastr[2] = seg_last[2]; }
         // input rows of the segment: virtual rows 2*first-2 .. 2*last+2 (reflected by the producer)
         vr0 = 2 * nextr[1] - 2;
         k_total = 2 * (lastr[1] - nextr[1] + 1) + 3;
         issued = 0;
         kcons = 0;
-        pend = -1;
+        pend_q = -1;
     }
 
-    // ---- levels >= 3: a finished row `r` of level l-1 sits in its shared ring ------------------
-    // ring row layout (float, per channel plane): [px -2, -1 | px 0 .. w-1 | px w, w+1]
+    // ---- levels >= 3, run by ONE warp per level-2 row (the warps take turns) --------------------
+    // Row r of level l-1 is complete in ring l-1 (slot r & 1; per channel plane: aprons at float
+    // 2,3 = px -2,-1, px p at float 4+p, aprons px w, w+1 behind).  A lane owns N = 64 >> l
+    // adjacent pixels of level l: horizontal pass into the H ring of level l (HR rows), then
+    // every level-l row whose five H rows are present is finished, written to ring l (or to
+    // global memory at the last level) and handed to level l+1 by the same warp: no block
+    // barrier anywhere above level 2.
     template <int l>
-    __device__ __forceinline__ void on_row(int r) {
-        const bool ownl = own && i < a.w[l];
-        const int hs = (hslot[l] == HR - 1) ? 0 : hslot[l] + 1;       // slot of source row r (rows arrive in order)
-        hslot[l] = hs;
-        const int ss = 3 * hps[l];
-        unsigned char* const hmine = smem + a.hring_off[l] + 4 * i;
-        if (ownl) {
-            const unsigned char* p = smem + a.ring_off[l - 1] + (r & 1) * 3 * rps[l - 1] + 8 * i;   // px 2i-2
-            unsigned char* hdst = hmine + hs * ss;
+    __device__ __forceinline__ void duty_row(int r) {
+        constexpr int N = 64 >> l;                 // 8, 4, 2, 1 pixels per lane
+        constexpr int C = N >= 4 ? 4 : N;          // pixels per vertical-pass chunk
+        DutyState* ds = duty_state();
+        const int lane = threadIdx.x & 31;
+        const int wl = a.w[l], hp = a.h[l - 1];
+        int hs = ds->hslot[l] + 1;
+        if (hs == HR) hs = 0;
+        float* const hring = reinterpret_cast<float*>(smem + a.hring_off[l]);
+        const float* const src = reinterpret_cast<const float*>(smem + a.ring_off[l - 1]) + (r & 1) * 3 * a.ring_stride[l - 1];
+        for (int px0 = lane * N; px0 < wl; px0 += 32 * N) {
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
-                const float2 ta = *reinterpret_cast<const float2*>(p);
-                const float2 tb = *reinterpret_cast<const float2*>(p + 8);
-                const float tc = *reinterpret_cast<const float*>(p + 16);
-                *reinterpret_cast<float*>(hdst) = tb.x * 6.0f + (ta.y + tb.y) * 4.0f + ta.x + tc;
-                p += rps[l - 1];
-                hdst += hps[l];
+                const float* p = src + ch * a.ring_stride[l - 1] + 2 * px0 + 2;     // px 2 px0 - 2
+                float x[2 * N + 4];
+                ldv<2>(p, x);
+                if constexpr (N >= 2) {
+#pragma unroll
+                    for (int k = 0; k < N / 2; ++k) ldv<4>(p + 2 + 4 * k, x + 2 + 4 * k);
+                } else {
+                    ldv<2>(p + 2, x + 2);
+                }
+                x[2 * N + 2] = p[2 * N + 2];
+                float o[N];
+#pragma unroll
+                for (int m = 0; m < N; ++m)
+                    o[m] = x[2 * m + 2] * 6.0f + (x[2 * m + 1] + x[2 * m + 3]) * 4.0f + x[2 * m] + x[2 * m + 4];
+                float* hd = hring + (hs * 3 + ch) * wl + px0;
+#pragma unroll
+                for (int k = 0; k < N; k += C) stv<C>(hd + k, o + k);
             }
         }
-        const int hp = a.h[l - 1];
-        while (nextr[l] <= lastr[l] && min(2 * nextr[l] + 2, hp - 1) <= r) {
-            const int q = nextr[l];
-            // H-ring slots of the five source rows: row r' sits (r - r') slots behind the newest
-            int so[5];
+        int nx = ds->nextr[l];
+        const int lst = ds->lastr[l];
+        __syncwarp();
+        while (nx <= lst && min(2 * nx + 2, hp - 1) <= r) {
+            const int q = nx;
+            int so[5];                              // H-ring rows of the five source rows: row r' sits (r - r') slots behind the newest
 #pragma unroll
             for (int d = 0; d < 5; ++d) {
                 int sl = hs - (r - vhr_reflect101(2 * q - 2 + d, hp));
                 if (sl < 0) sl += HR;
-                so[d] = sl * ss;
+                so[d] = sl * 3 * wl;
             }
-            if (ownl) {
-                float v[3];
+            float* const dring = (l < L) ? reinterpret_cast<float*>(smem + a.ring_off[l < L ? l : 2]) + (q & 1) * 3 * a.ring_stride[l < L ? l : 2] : nullptr;
+            for (int px0 = lane * C; px0 < wl; px0 += 32 * C) {
+                float v[3][C];
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {
-                    const unsigned char* hc = hmine + ch * hps[l];
-                    const float sum = *reinterpret_cast<const float*>(hc + so[2]) * 6.0f +
-                                      (*reinterpret_cast<const float*>(hc + so[1]) + *reinterpret_cast<const float*>(hc + so[3])) * 4.0f +
-                                      *reinterpret_cast<const float*>(hc + so[0]) + *reinterpret_cast<const float*>(hc + so[4]);
-                    v[ch] = sum * (1.0f / 256.0f);
+                    const float* hc = hring + ch * wl + px0;
+                    float t0[C], t1[C], t2[C], t3[C], t4[C];
+                    ldv<C>(hc + so[0], t0); ldv<C>(hc + so[1], t1); ldv<C>(hc + so[2], t2);
+                    ldv<C>(hc + so[3], t3); ldv<C>(hc + so[4], t4);
+#pragma unroll
+                    for (int m = 0; m < C; ++m)
+                        v[ch][m] = (t2[m] * 6.0f + (t1[m] + t3[m]) * 4.0f + t0[m] + t4[m]) * (1.0f / 256.0f);
                 }
                 if constexpr (l == L) {
-                    float* o = out_frame + ((size_t)q * a.w[l] + i) * 3;
-                    o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
+                    float t[3 * C];
+#pragma unroll
+                    for (int m = 0; m < C; ++m) { t[3 * m] = v[0][m]; t[3 * m + 1] = v[1][m]; t[3 * m + 2] = v[2][m]; }
+                    float* o = out_frame + ((size_t)q * wl + px0) * 3;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) stv<C>(o + C * k, t + C * k);
                 } else {
-                    unsigned char* const dst = smem + a.ring_off[l] + (q & 1) * 3 * rps[l];
 #pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) *reinterpret_cast<float*>(dst + ch * rps[l] + 8 + 4 * i) = v[ch];
-                    const uint32_t am = (apron >> (4 * (l - 2))) & 15u;
-                    if (am) {
-#pragma unroll
-                        for (int ch = 0; ch < 3; ++ch) {
-                            float* pl = reinterpret_cast<float*>(dst + ch * rps[l]);
-                            if (am & 1u) pl[0] = v[ch];
-                            if (am & 2u) pl[1] = v[ch];
-                            if (am & 4u) pl[2 + a.w[l]] = v[ch];
-                            if (am & 8u) pl[3 + a.w[l]] = v[ch];
-                        }
-                    }
+                    for (int ch = 0; ch < 3; ++ch) stv<C>(dring + ch * a.ring_stride[l] + 4 + px0, v[ch]);
                 }
             }
-            nextr[l] = q + 1;
+            nx = q + 1;
             if constexpr (l < L) {
-                __syncthreads();                    // row q of level l visible to the neighbours
-                on_row<l + 1>(q);
+                __syncwarp();
+                if (lane < 3) {                     // reflect-101 aprons of the new row, one channel per lane
+                    float* pl = dring + lane * a.ring_stride[l];
+                    pl[2] = pl[4 + vhr_reflect101(-2, wl)];
+                    pl[3] = pl[4 + vhr_reflect101(-1, wl)];
+                    pl[4 + wl] = pl[4 + vhr_reflect101(wl, wl)];
+                    pl[5 + wl] = pl[4 + vhr_reflect101(wl + 1, wl)];
+                }
+                __syncwarp();
+                duty_row<l + 1>(q);
             }
         }
+        __syncwarp();
+        if (lane == 0) { ds->hslot[l] = hs; ds->nextr[l] = nx; }
     }
 
     // ---- level 2: vertical pass + hand-over --------------------------------------------------
@@ -335,18 +384,40 @@ struct Stream {
             f[k] = (float)s * (1.0f / 65536.0f);
         }
     }
-    // The row barrier of level-2 row `pend`: every warp has signalled it -> its consumers run now,
-    // and the input rows read before that signal may be recycled.
-    __device__ __forceinline__ void drain() {
-        if (pend < 0) return;
-        mbar_wait(bar0 + 8 * a.nr, (uint32_t)rb_phase);
-        rb_phase ^= 1;
-        refill(kc_arr);
-        if constexpr (L >= 3) on_row<3>(pend);
-        pend = -1;
+    // The warp whose turn it is for level-2 row q (turns rotate so that the heavier rows, which
+    // also finish rows of the upper levels, do not always fall on the same warps).
+    __device__ __forceinline__ bool my_turn(int q) const {
+        const int nw = blockDim.x >> 5;
+        return (q + q / nw) % nw == (int)(threadIdx.x >> 5);
+    }
+    // Upper levels of level-2 row (q, number n), by the warp whose turn it is: the row must be
+    // complete and the previous row's upper-level work done (shared H rings, DutyState).
+    // (wait_row(n) must come BEFORE this warp signals row n + 1: a parity wait may lag the barrier by
+    // one phase only.)
+    __device__ __forceinline__ void run_duty(int q, int n, bool row_waited) {
+        if constexpr (L >= 3) {
+            if (q < 0 || !my_turn(q)) return;
+            if (!row_waited) wait_row(n);
+            if (n >= 1) wait_duty(n - 1);
+            duty_row<3>(q);
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0)
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar0 + 8 * (a.nr + 1 + (n & 1))) : "memory");
+        }
+    }
+    // Warp 0, half a row after publishing row pend_n: recycle the input rows everybody has read.
+    __device__ __forceinline__ void refill_after_row() {
+        if (threadIdx.x < 32 && pend_q >= 0) {
+            wait_row(pend_n);
+            refill(kc_arr);
+        }
     }
     __device__ __forceinline__ void publish(int q, const float (&f)[6]) {
-        drain();
+        if constexpr (L >= 3) {
+            if (dn >= 2) wait_duty(dn - 2);          // the ring slot's previous row has been consumed
+        }
+        // An mbarrier counts arrivals, not warps: nobody may signal row n before row n-1 is complete.
+        if (pend_q >= 0) wait_row(pend_n);
         if (own) {
             if constexpr (L == 2) {
                 float2* o = reinterpret_cast<float2*>(out_frame + ((size_t)q * a.w[2] + 2 * i) * 3);
@@ -354,31 +425,41 @@ struct Stream {
                 o[1] = make_float2(f[4], f[1]);      //        c2 | px 2i+1: c0
                 o[2] = make_float2(f[3], f[5]);      //        c1 c2
             } else {
-                unsigned char* const dst = smem + a.ring_off[2] + (q & 1) * 3 * rps[2];
+                float* const dst = reinterpret_cast<float*>(smem + a.ring_off[2]) + (q & 1) * 3 * a.ring_stride[2];
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch)
-                    *reinterpret_cast<float2*>(dst + ch * rps[2] + 8 + 8 * i) = make_float2(f[2 * ch], f[2 * ch + 1]);
+                    *reinterpret_cast<float2*>(dst + ch * a.ring_stride[2] + 4 + 2 * i) = make_float2(f[2 * ch], f[2 * ch + 1]);
                 if (i <= 1 || last_col) {            // aprons: px -2 <- px 2, px -1 <- px 1, px w2 <- px w2-2
 #pragma unroll
                     for (int ch = 0; ch < 3; ++ch) {
-                        float* pl = reinterpret_cast<float*>(dst + ch * rps[2]);
-                        if (i == 1) pl[0] = f[2 * ch];
-                        if (i == 0) pl[1] = f[2 * ch + 1];
-                        if (last_col) pl[2 + a.w[2]] = f[2 * ch];
+                        float* pl = dst + ch * a.ring_stride[2];
+                        if (i == 1) pl[2] = f[2 * ch];
+                        if (i == 0) pl[3] = f[2 * ch + 1];
+                        if (last_col) pl[4 + a.w[2]] = f[2 * ch];
                     }
                 }
             }
         }
         __syncwarp();
         if ((threadIdx.x & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar0 + 8 * a.nr) : "memory");
+        const int pq = pend_q, pn = pend_n;
         kc_arr = kcons;
-        pend = q;
+        pend_q = q;
+        pend_n = dn++;
         nextr[2] = q + 1;
+        run_duty(pq, pn, true);                      // the previous row: nobody waits for its upper levels yet
     }
 
     // ---- one segment ----------------------------------------------------------------------------
     __device__ __forceinline__ void run_segment() {
-        sync_refill();
+        sync_refill();                  // every warp is done with the previous segment
+        if constexpr (L >= 3) {
+            if (threadIdx.x == 0) {
+                DutyState* ds = duty_state();
+#pragma unroll
+                for (int l = 3; l <= L; ++l) { ds->nextr[l] = seg_next[l]; ds->lastr[l] = seg_last[l]; }
+            }
+        }
         prime();
         sync_refill();
         if constexpr (L == 1) {
@@ -428,7 +509,7 @@ struct Stream {
 #pragma unroll
                     for (int k = 0; k < 6; ++k) x3[k] = x1[k];          // row h1 reflects to h1-2 = 2q-1
                 }
-                drain();                                               // consumers of level-2 row q-1
+                refill_after_row();
                 if (has2) {
                     l12_row(x4);
                 } else {
@@ -441,7 +522,8 @@ struct Stream {
                 for (int k = 0; k < 6; ++k) { x0[k] = x2[k]; x1[k] = x3[k]; x2[k] = x4[k]; }
                 publish(q, f);
             }
-            drain();
+            refill_after_row();
+            run_duty(pend_q, pend_n, false);         // the last row of the segment
         }
     }
 };
@@ -455,6 +537,10 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) pyrdown_stream_kern
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.nr; ++s) mbar_init(smem_u32(smem) + 8 * s, 1);
         mbar_init(smem_u32(smem) + 8 * a.nr, blockDim.x >> 5);         // row barrier: one arrival per warp
+        mbar_init(smem_u32(smem) + 8 * (a.nr + 1), 1);                 // duty barriers: one arrival per row
+        mbar_init(smem_u32(smem) + 8 * (a.nr + 2), 1);
+        DutyState* ds = reinterpret_cast<DutyState*>(smem + a.duty_off);
+        for (int l = 0; l <= VHR_MAX_LEVELS; ++l) { ds->hslot[l] = 0; ds->nextr[l] = 0; ds->lastr[l] = -1; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     const int col = (int)(threadIdx.x >> 5) * LANES + (int)(threadIdx.x & 31) - 1;
@@ -504,8 +590,9 @@ int dispatch_stream(vhr_ctx* ctx, const StreamArgs& a, int threads, int smem_byt
 int vhr_pyrdown_stream(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int W, int levels, float* d_level,
                        cudaStream_t stream) {
     if (W % 16 != 0 || W > 8 * LANES * 16 || (reinterpret_cast<uintptr_t>(d_frames) & 15) != 0 ||
-        (reinterpret_cast<uintptr_t>(d_level) & 7) != 0)
+        (reinterpret_cast<uintptr_t>(d_level) & 15) != 0)
         return VHR_ERR_UNSUPPORTED;
+    if (levels >= 3 && W % 64 != 0) return VHR_ERR_UNSUPPORTED;     // a lane of the upper-level warp owns 64 >> l pixels
     StreamArgs a;
     memset(&a, 0, sizeof(a));
     a.frames = d_frames; a.out = d_level; a.T = T; a.H = H; a.W = W; a.levels = levels;
@@ -520,7 +607,7 @@ int vhr_pyrdown_stream(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int 
     auto al16 = [](int v) { return (v + 15) & ~15; };
     int fixed = 0;                                                  // everything but the input ring
     for (int l = 2; l < levels; ++l) {
-        a.ring_stride[l] = (a.w[l] + 4 + 3) & ~3;                   // 2 + 2 apron cells
+        a.ring_stride[l] = (a.w[l] + 8 + 3) & ~3;                   // px p at float 4 + p; aprons at 2, 3 and w + 4, w + 5
         fixed = al16(fixed + 2 * 3 * a.ring_stride[l] * 4);
     }
     for (int l = 3; l <= levels; ++l) fixed = al16(fixed + HR * 3 * a.w[l] * 4);
@@ -528,10 +615,12 @@ int vhr_pyrdown_stream(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int 
     const int budget = (threads <= 256 ? ctx->smem_optin / 2 - 2048 : ctx->smem_optin - 1024);
     // (the deferred row barrier needs >= 7 rows: up to 6 are consumed between two refills)
     int nr = 12;
-    while (nr > 7 && al16(8 * (nr + 1)) + 32 + nr * a.rowbytes + fixed > budget) --nr;
-    if (al16(8 * (nr + 1)) + 32 + nr * a.rowbytes + fixed > ctx->smem_optin) return VHR_ERR_UNSUPPORTED;
+    const int head = 8 * 16 + (int)sizeof(DutyState) + 16;          // barriers (<= 13), DutyState
+    while (nr > 7 && al16(head) + 32 + nr * a.rowbytes + fixed > budget) --nr;
+    if (al16(head) + 32 + nr * a.rowbytes + fixed > ctx->smem_optin) return VHR_ERR_UNSUPPORTED;
     a.nr = nr;
-    int off = al16(8 * (nr + 1));
+    a.duty_off = 8 * 16;
+    int off = al16(head);
     a.in_off = off + 16;
     off = al16(a.in_off + nr * a.rowbytes + 16);
     for (int l = 2; l < levels; ++l) {
