@@ -25,6 +25,9 @@ namespace {
 
 constexpr int HR = 5;        // rows in a private H ring (exactly the vertical footprint)
 constexpr int LANES = 30;    // column groups per warp (lanes 1..30); lanes 0 / 31 are halo lanes
+constexpr int WSLOT = 784;   // bytes of one input row in a warp's ring: 32 column groups x 24 B + 8 B either side, 16-B multiple
+constexpr int RS = 4;        // level-2 ring slots = rows a warp may run ahead of the upper levels
+constexpr int DLY = 2;       // the upper levels of row n start when their warp has published row n + DLY
 
 struct StreamArgs {
     const uint8_t* frames;
@@ -34,9 +37,10 @@ struct StreamArgs {
     int h[VHR_MAX_LEVELS + 1];
     long long total_rows;
     int nt;                                // column groups = W / 8
-    int nr;                                // rows in the input ring
+    int nr;                                // rows in each warp's input ring
     int rowbytes;                          // 3 W
-    int in_off;                            // byte offset of ring row 0 (16 bytes of slack either side of the ring)
+    int in_off;                            // byte offset of warp 0's input ring (warp w: + w * nr * WSLOT)
+    int rbar_off;                          // byte offset of the RS row barriers, followed by the RS duty barriers
     int ring_off[VHR_MAX_LEVELS + 1];      // levels 2..L-1: newest rows, float planar, double-buffered
     int ring_stride[VHR_MAX_LEVELS + 1];   // floats per channel plane row
     int hring_off[VHR_MAX_LEVELS + 1];     // levels 3..L: H rings (HR rows x 3 planes x w[l])
@@ -146,17 +150,17 @@ struct Stream {
     const int i;              // column group of this lane (-1 / >= nt on idle halo lanes)
     const bool own;           // lane owns outputs of column group i
     const bool first_col, last_col;
-    const unsigned char* rd;  // smem + in_off + 24 * clamp(i) - 8
-    uint32_t bar0;            // shared address of mbarrier 0 (input ring: nr barriers; then the row barrier)
-    // input ring, consumer side (block-uniform)
+    const unsigned char* rd;  // this lane's 36 bytes in slot 0 of the warp's input ring
+    uint32_t bar0;            // shared address of mbarrier 0
+    uint32_t wbar;            // shared address of the warp's slot-0 "row landed" barrier
+    // the warp's input ring: consumer side (all lanes) and producer side (lane 0)
     int c_slot, c_phase, kcons;
-    // producer side (thread 0)
     int p_slot, issued, k_total, vr0;
-    // rows of level 2 are numbered across segments (dn = rows published so far, the same in every
-    // warp).  Row barrier: phase n completes when every warp has written its part of row n.
-    // Duty barriers (two, alternating): phase n >> 1 of barrier n & 1 completes when the upper
-    // levels have consumed row n.
-    int dn, pend_q, pend_n, kc_arr;
+    int src_off, cp_bytes, dst_off;        // the warp's byte range of an input row
+    // Rows of level 2 are numbered across segments (dn = rows published so far, the same in every
+    // warp).  Row barrier n % RS, phase n / RS: every warp has written its part of row n.
+    // Duty barrier n % RS, phase n / RS: the upper levels have consumed row n.
+    int dn, seg_n0, seg_q0;
     const uint8_t* frame;
     float* out_frame;
     int nextr[3], lastr[3];            // levels 1, 2 (levels >= 3: DutyState)
@@ -166,40 +170,43 @@ struct Stream {
     __device__ Stream(const StreamArgs& a_, unsigned char* s, int col)
         : a(a_), smem(s), i(col), own((threadIdx.x & 31) >= 1 && (threadIdx.x & 31) <= LANES && col < a_.nt),
           first_col(col == 0), last_col(col == a_.nt - 1) {
-        const int ic = min(max(col, 0), a.nt - 1);
-        rd = smem + a.in_off + 24 * ic - 8;
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        rd = smem + a.in_off + warp * a.nr * WSLOT + 24 * lane;
         bar0 = smem_u32(smem);
+        wbar = bar0 + 8 * warp * a.nr;
         c_slot = 0; c_phase = 0; kcons = 0; p_slot = 0; issued = 0; k_total = 0; vr0 = 0;
-        dn = 0; pend_q = -1; pend_n = -1; kc_arr = 0;
+        // slot byte b of the warp <-> byte 24 * LANES * warp - 32 + b of the input row
+        const int lo = 24 * LANES * warp - 32;
+        src_off = max(lo, 0);
+        dst_off = src_off - lo;
+        cp_bytes = min(a.rowbytes, lo + WSLOT) - src_off;
+        dn = 0; seg_n0 = 0; seg_q0 = 0;
     }
-    __device__ __forceinline__ void wait_row(int n) { mbar_wait(bar0 + 8 * a.nr, (uint32_t)(n & 1)); }
-    __device__ __forceinline__ void wait_duty(int n) { mbar_wait(bar0 + 8 * (a.nr + 1 + (n & 1)), (uint32_t)((n >> 1) & 1)); }
     __device__ __forceinline__ DutyState* duty_state() const { return reinterpret_cast<DutyState*>(smem + a.duty_off); }
+    __device__ __forceinline__ void wait_row(int n) { mbar_wait(bar0 + a.rbar_off + 8 * (n & (RS - 1)), (uint32_t)((n / RS) & 1)); }
+    __device__ __forceinline__ void wait_duty(int n) { mbar_wait(bar0 + a.rbar_off + 8 * (RS + (n & (RS - 1))), (uint32_t)((n / RS) & 1)); }
 
-    // ---- input ring -------------------------------------------------------------------------
-    // Rows [0, done) of the segment have been read by every thread: their slots may be refilled.
-    __device__ __forceinline__ void refill(int done) {
-        if (threadIdx.x == 0) {
-            const int lim = min(k_total, done + a.nr);
+    // ---- the warp's input ring ------------------------------------------------------------------
+    // Every row the warp has consumed so far (kcons) has been read by all its lanes: lane 0
+    // requests the next rows into those slots.
+    __device__ __forceinline__ void refill() {
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) {
+            const int lim = min(k_total, kcons + a.nr);
             while (issued < lim) {
                 const int row = vhr_reflect101(vr0 + issued, a.H);
-                const uint32_t bar = bar0 + 8 * p_slot;
-                mbar_expect_tx(bar, (uint32_t)a.rowbytes);
-                bulk_g2s(smem_u32(smem + a.in_off + p_slot * a.rowbytes), frame + (size_t)row * a.rowbytes,
-                         (uint32_t)a.rowbytes, bar);
+                const uint32_t bar = wbar + 8 * p_slot;
+                mbar_expect_tx(bar, (uint32_t)cp_bytes);
+                bulk_g2s(smem_u32(rd) + p_slot * WSLOT + dst_off, frame + (size_t)row * a.rowbytes + src_off, (uint32_t)cp_bytes, bar);
                 p_slot = (p_slot + 1 == a.nr) ? 0 : p_slot + 1;
                 ++issued;
             }
         }
     }
-    __device__ __forceinline__ void sync_refill() {
-        __syncthreads();
-        refill(kcons);
-    }
     // Next input row of the segment -> its level-1 horizontal pass (6 packed registers).
     __device__ __forceinline__ void consume(uint32_t (&hp)[6]) {
-        mbar_wait(bar0 + 8 * c_slot, (uint32_t)c_phase);
-        const unsigned char* p = rd + c_slot * a.rowbytes;
+        mbar_wait(wbar + 8 * c_slot, (uint32_t)c_phase);
+        const unsigned char* p = rd + c_slot * WSLOT;
         uint32_t wd[9];
         const uint2 q0 = *reinterpret_cast<const uint2*>(p), q1 = *reinterpret_cast<const uint2*>(p + 8);
         const uint2 q2 = *reinterpret_cast<const uint2*>(p + 16), q3 = *reinterpret_cast<const uint2*>(p + 24);
@@ -225,6 +232,7 @@ struct Stream {
 #pragma unroll
             for (int k = 0; k < 6; ++k) { w0[k] = w1[k]; w1[k] = w2[k]; w2[k] = hn[k]; }
         }
+        refill();
     }
     __device__ __forceinline__ void l1_row(uint32_t (&v)[6]) {
         uint32_t w3[6], w4[6];
@@ -277,7 +285,8 @@ struct Stream {
         k_total = 2 * (lastr[1] - nextr[1] + 1) + 3;
         issued = 0;
         kcons = 0;
-        pend_q = -1;
+        seg_n0 = dn;
+        seg_q0 = (L >= 2) ? nextr[L >= 2 ? 2 : 1] : 0;
     }
 
     // ---- levels >= 3, run by ONE warp per level-2 row (the warps take turns) --------------------
@@ -288,7 +297,7 @@ struct Stream {
     // global memory at the last level) and handed to level l+1 by the same warp: no block
     // barrier anywhere above level 2.
     template <int l>
-    __device__ __forceinline__ void duty_row(int r) {
+    __device__ __forceinline__ void duty_row(int r, int src_slot) {
         constexpr int N = 64 >> l;                 // 8, 4, 2, 1 pixels per lane
         constexpr int C = N >= 4 ? 4 : N;          // pixels per vertical-pass chunk
         DutyState* ds = duty_state();
@@ -297,7 +306,7 @@ struct Stream {
         int hs = ds->hslot[l] + 1;
         if (hs == HR) hs = 0;
         float* const hring = reinterpret_cast<float*>(smem + a.hring_off[l]);
-        const float* const src = reinterpret_cast<const float*>(smem + a.ring_off[l - 1]) + (r & 1) * 3 * a.ring_stride[l - 1];
+        const float* const src = reinterpret_cast<const float*>(smem + a.ring_off[l - 1]) + src_slot * 3 * a.ring_stride[l - 1];
         for (int px0 = lane * N; px0 < wl; px0 += 32 * N) {
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
@@ -368,7 +377,7 @@ struct Stream {
                     pl[5 + wl] = pl[4 + vhr_reflect101(wl + 1, wl)];
                 }
                 __syncwarp();
-                duty_row<l + 1>(q);
+                duty_row<l + 1>(q, q & 1);
             }
         }
         __syncwarp();
@@ -390,34 +399,30 @@ struct Stream {
         const int nw = blockDim.x >> 5;
         return (q + q / nw) % nw == (int)(threadIdx.x >> 5);
     }
-    // Upper levels of level-2 row (q, number n), by the warp whose turn it is: the row must be
-    // complete and the previous row's upper-level work done (shared H rings, DutyState).
-    // (wait_row(n) must come BEFORE this warp signals row n + 1: a parity wait may lag the barrier by
-    // one phase only.)
-    __device__ __forceinline__ void run_duty(int q, int n, bool row_waited) {
+    // Upper levels of level-2 row number n of this segment, by the warp whose turn it is: the row
+    // must be complete and the previous row's upper-level work done (shared H rings, DutyState).
+    // Every parity wait below lags its barrier by less than one phase: the next phase of row
+    // barrier n % RS needs this warp's signal for row n + RS, which follows duty(n) in program
+    // order via the slot wait in publish(); the next phase of duty barrier (n-1) % RS needs duty(n).
+    __device__ __forceinline__ void run_duty(int n) {
         if constexpr (L >= 3) {
-            if (q < 0 || !my_turn(q)) return;
-            if (!row_waited) wait_row(n);
+            const int q = seg_q0 + (n - seg_n0);
+            if (!my_turn(q)) return;
+            wait_row(n);
             if (n >= 1) wait_duty(n - 1);
-            duty_row<3>(q);
+            duty_row<3>(q, n & (RS - 1));
             __syncwarp();
             if ((threadIdx.x & 31) == 0)
-                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar0 + 8 * (a.nr + 1 + (n & 1))) : "memory");
-        }
-    }
-    // Warp 0, half a row after publishing row pend_n: recycle the input rows everybody has read.
-    __device__ __forceinline__ void refill_after_row() {
-        if (threadIdx.x < 32 && pend_q >= 0) {
-            wait_row(pend_n);
-            refill(kc_arr);
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar0 + a.rbar_off + 8 * (RS + (n & (RS - 1)))) : "memory");
         }
     }
     __device__ __forceinline__ void publish(int q, const float (&f)[6]) {
+        const int n = dn;
         if constexpr (L >= 3) {
-            if (dn >= 2) wait_duty(dn - 2);          // the ring slot's previous row has been consumed
+            // the ring slot's previous row (n - RS) has been consumed; this also keeps the signals of
+            // row n out of the row barrier's previous phase
+            if (n >= RS) wait_duty(n - RS);
         }
-        // An mbarrier counts arrivals, not warps: nobody may signal row n before row n-1 is complete.
-        if (pend_q >= 0) wait_row(pend_n);
         if (own) {
             if constexpr (L == 2) {
                 float2* o = reinterpret_cast<float2*>(out_frame + ((size_t)q * a.w[2] + 2 * i) * 3);
@@ -425,7 +430,7 @@ struct Stream {
                 o[1] = make_float2(f[4], f[1]);      //        c2 | px 2i+1: c0
                 o[2] = make_float2(f[3], f[5]);      //        c1 c2
             } else {
-                float* const dst = reinterpret_cast<float*>(smem + a.ring_off[2]) + (q & 1) * 3 * a.ring_stride[2];
+                float* const dst = reinterpret_cast<float*>(smem + a.ring_off[2]) + (n & (RS - 1)) * 3 * a.ring_stride[2];
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch)
                     *reinterpret_cast<float2*>(dst + ch * a.ring_stride[2] + 4 + 2 * i) = make_float2(f[2 * ch], f[2 * ch + 1]);
@@ -440,28 +445,29 @@ struct Stream {
                 }
             }
         }
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar0 + 8 * a.nr) : "memory");
-        const int pq = pend_q, pn = pend_n;
-        kc_arr = kcons;
-        pend_q = q;
-        pend_n = dn++;
+        if constexpr (L >= 3) {
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0)
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar0 + a.rbar_off + 8 * (n & (RS - 1))) : "memory");
+        }
+        dn = n + 1;
         nextr[2] = q + 1;
-        run_duty(pq, pn, true);                      // the previous row: nobody waits for its upper levels yet
+        if (n - DLY >= seg_n0) run_duty(n - DLY);    // an older row: complete by now, and nobody waits for its upper levels yet
     }
 
     // ---- one segment ----------------------------------------------------------------------------
     __device__ __forceinline__ void run_segment() {
-        sync_refill();                  // every warp is done with the previous segment
+        __syncthreads();                // every warp is done with the previous segment (upper levels included)
         if constexpr (L >= 3) {
             if (threadIdx.x == 0) {
                 DutyState* ds = duty_state();
 #pragma unroll
                 for (int l = 3; l <= L; ++l) { ds->nextr[l] = seg_next[l]; ds->lastr[l] = seg_last[l]; }
             }
+            __syncthreads();
         }
+        refill();
         prime();
-        sync_refill();
         if constexpr (L == 1) {
             int n = 0;
             for (int r = nextr[1]; r <= lastr[1]; ++r) {
@@ -477,7 +483,7 @@ struct Stream {
                         o[9 + ch] = (float)(v[2 * ch + 1] >> 16) * (1.0f / 256.0f);
                     }
                 }
-                if (++n == 2) { n = 0; sync_refill(); }
+                if (++n == 2) { n = 0; refill(); }
             }
         } else {
             const int h1 = a.h[1];
@@ -491,7 +497,7 @@ struct Stream {
                 l12_row(o);
 #pragma unroll
                 for (int k = 0; k < 6; ++k) { x0[k] = x1[k]; x1[k] = x2[k]; x2[k] = o[k]; }
-                sync_refill();
+                refill();
             }
             if (q == 0) {                            // rows -2,-1 reflect to 2,1
                 float f[6];
@@ -509,7 +515,6 @@ struct Stream {
 #pragma unroll
                     for (int k = 0; k < 6; ++k) x3[k] = x1[k];          // row h1 reflects to h1-2 = 2q-1
                 }
-                refill_after_row();
                 if (has2) {
                     l12_row(x4);
                 } else {
@@ -520,10 +525,10 @@ struct Stream {
                 l2_vpass(x0, x1, x2, x3, x4, f);
 #pragma unroll
                 for (int k = 0; k < 6; ++k) { x0[k] = x2[k]; x1[k] = x3[k]; x2[k] = x4[k]; }
+                refill();
                 publish(q, f);
             }
-            refill_after_row();
-            run_duty(pend_q, pend_n, false);         // the last row of the segment
+            for (int n = max(dn - DLY, seg_n0); n < dn; ++n) run_duty(n);    // the last rows of the segment
         }
     }
 };
@@ -535,10 +540,12 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) pyrdown_stream_kern
     const long long hi = a.total_rows * (blockIdx.x + 1) / gridDim.x;
     if (lo >= hi) return;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < a.nr; ++s) mbar_init(smem_u32(smem) + 8 * s, 1);
-        mbar_init(smem_u32(smem) + 8 * a.nr, blockDim.x >> 5);         // row barrier: one arrival per warp
-        mbar_init(smem_u32(smem) + 8 * (a.nr + 1), 1);                 // duty barriers: one arrival per row
-        mbar_init(smem_u32(smem) + 8 * (a.nr + 2), 1);
+        const int nw = blockDim.x >> 5;
+        for (int b = 0; b < nw * a.nr; ++b) mbar_init(smem_u32(smem) + 8 * b, 1);             // rows landed, per warp and slot
+        for (int b = 0; b < RS; ++b) {
+            mbar_init(smem_u32(smem) + a.rbar_off + 8 * b, nw);                                // row barriers: one arrival per warp
+            mbar_init(smem_u32(smem) + a.rbar_off + 8 * (RS + b), 1);                          // duty barriers: one arrival per row
+        }
         DutyState* ds = reinterpret_cast<DutyState*>(smem + a.duty_off);
         for (int l = 0; l <= VHR_MAX_LEVELS; ++l) { ds->hslot[l] = 0; ds->nextr[l] = 0; ds->lastr[l] = -1; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -605,27 +612,27 @@ int vhr_pyrdown_stream(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int 
     const int warps = (a.nt + LANES - 1) / LANES;
     const int threads = warps * 32;
     auto al16 = [](int v) { return (v + 15) & ~15; };
-    int fixed = 0;                                                  // everything but the input ring
+    int fixed = 0;                                                  // everything but the input rings
     for (int l = 2; l < levels; ++l) {
         a.ring_stride[l] = (a.w[l] + 8 + 3) & ~3;                   // px p at float 4 + p; aprons at 2, 3 and w + 4, w + 5
-        fixed = al16(fixed + 2 * 3 * a.ring_stride[l] * 4);
+        fixed = al16(fixed + (l == 2 ? RS : 2) * 3 * a.ring_stride[l] * 4);
     }
     for (int l = 3; l <= levels; ++l) fixed = al16(fixed + HR * 3 * a.w[l] * 4);
-    // input ring depth: as deep as two CTAs per SM allow (12 rows = 8..12 rows of HBM requests in flight per CTA)
+    // per-warp input rings: as deep as two CTAs per SM allow (at most 4 rows are consumed between two refills)
     const int budget = (threads <= 256 ? ctx->smem_optin / 2 - 2048 : ctx->smem_optin - 1024);
-    // (the deferred row barrier needs >= 7 rows: up to 6 are consumed between two refills)
     int nr = 12;
-    const int head = 8 * 16 + (int)sizeof(DutyState) + 16;          // barriers (<= 13), DutyState
-    while (nr > 7 && al16(head) + 32 + nr * a.rowbytes + fixed > budget) --nr;
-    if (al16(head) + 32 + nr * a.rowbytes + fixed > ctx->smem_optin) return VHR_ERR_UNSUPPORTED;
+    auto head = [&](int n) { return al16(8 * (warps * n + 2 * RS)) + al16((int)sizeof(DutyState)); };
+    while (nr > 6 && head(nr) + warps * nr * WSLOT + fixed > budget) --nr;
+    if (head(nr) + warps * nr * WSLOT + fixed > ctx->smem_optin) return VHR_ERR_UNSUPPORTED;
     a.nr = nr;
-    a.duty_off = 8 * 16;
-    int off = al16(head);
-    a.in_off = off + 16;
-    off = al16(a.in_off + nr * a.rowbytes + 16);
+    a.rbar_off = 8 * warps * nr;
+    a.duty_off = al16(8 * (warps * nr + 2 * RS));
+    int off = head(nr);
+    a.in_off = off;
+    off = al16(off + warps * nr * WSLOT);
     for (int l = 2; l < levels; ++l) {
         a.ring_off[l] = off;
-        off = al16(off + 2 * 3 * a.ring_stride[l] * 4);
+        off = al16(off + (l == 2 ? RS : 2) * 3 * a.ring_stride[l] * 4);
     }
     for (int l = 3; l <= levels; ++l) {
         a.hring_off[l] = off;
