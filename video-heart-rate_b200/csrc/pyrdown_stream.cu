@@ -20,12 +20,15 @@
 //     shared memory, newest finished row per level double-buffered, one barrier per produced row.
 //   * Persistent grid over the flattened (frame, final-row) space, equal contiguous shares.
 #include "common.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
 
 namespace {
 
 constexpr int HR = 5;        // rows in a private H ring (exactly the vertical footprint)
 constexpr int LANES = 30;    // column groups per warp (lanes 1..30); lanes 0 / 31 are halo lanes
-constexpr int WSLOT = 784;   // bytes of one input row in a warp's ring: 32 column groups x 24 B + 8 B either side, 16-B multiple
+constexpr int WSLOT = 832;   // bytes of one input row in a warp's ring (>= 32 column groups x 24 B + 8 B either side)
+constexpr int GBYTES = 2 * WSLOT;   // input rows travel in groups of two = one TMA box, a multiple of 128 bytes
 constexpr int RS = 4;        // level-2 ring slots = rows a warp may run ahead of the upper levels
 constexpr int DLY = 2;       // the upper levels of row n start when their warp has published row n + DLY
 
@@ -37,9 +40,9 @@ struct StreamArgs {
     int h[VHR_MAX_LEVELS + 1];
     long long total_rows;
     int nt;                                // column groups = W / 8
-    int nr;                                // rows in each warp's input ring
+    int ng;                                // two-row groups in each warp's input ring
     int rowbytes;                          // 3 W
-    int in_off;                            // byte offset of warp 0's input ring (warp w: + w * nr * WSLOT)
+    int in_off;                            // byte offset of warp 0's input ring (warp w: + w * ng * GBYTES), 128-B aligned
     int rbar_off;                          // byte offset of the RS row barriers, followed by the RS duty barriers
     int ring_off[VHR_MAX_LEVELS + 1];      // levels 2..L-1: newest rows, float planar, double-buffered
     int ring_stride[VHR_MAX_LEVELS + 1];   // floats per channel plane row
@@ -76,6 +79,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {}
 }
 #endif
+__device__ __forceinline__ void tensor_g2s(uint32_t dst, const CUtensorMap* tmap, int x, int y, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -146,67 +153,82 @@ struct DutyState {
 template <int L>
 struct Stream {
     const StreamArgs& a;
+    const CUtensorMap* tmap;
     unsigned char* smem;
     const int i;              // column group of this lane (-1 / >= nt on idle halo lanes)
     const bool own;           // lane owns outputs of column group i
     const bool first_col, last_col;
-    const unsigned char* rd;  // this lane's 36 bytes in slot 0 of the warp's input ring
+    const unsigned char* rd;  // this lane's 36 bytes in row 0 of the warp's input ring
     uint32_t bar0;            // shared address of mbarrier 0
-    uint32_t wbar;            // shared address of the warp's slot-0 "row landed" barrier
-    // the warp's input ring: consumer side (all lanes) and producer side (lane 0)
-    int c_slot, c_phase, kcons;
-    int p_slot, issued, k_total, vr0;
-    int src_off, cp_bytes, dst_off;        // the warp's byte range of an input row
+    uint32_t wbar;            // shared address of the warp's group-0 "rows landed" barrier
+    // the warp's input ring: consumer side (all lanes) and producer side (lane 0); unit = group of two rows
+    int c_g, c_phase, g_cons;
+    int p_g, g_issued, g_total, vg0, frame_row0;
+    int src_off, cp_bytes, dst_off, box_x;        // the warp's byte range of an input row
     // Rows of level 2 are numbered across segments (dn = rows published so far, the same in every
     // warp).  Row barrier n % RS, phase n / RS: every warp has written its part of row n.
     // Duty barrier n % RS, phase n / RS: the upper levels have consumed row n.
     int dn, seg_n0, seg_q0;
+    int duty_m, turn_w, turn_c;        // next row handed to run_duty, and the warp whose turn it is
     const uint8_t* frame;
     float* out_frame;
     int nextr[3], lastr[3];            // levels 1, 2 (levels >= 3: DutyState)
     int seg_next[VHR_MAX_LEVELS + 1], seg_last[VHR_MAX_LEVELS + 1];
     uint32_t w0[6], w1[6], w2[6];      // level-1 H rows carried between level-1 rows
 
-    __device__ Stream(const StreamArgs& a_, unsigned char* s, int col)
-        : a(a_), smem(s), i(col), own((threadIdx.x & 31) >= 1 && (threadIdx.x & 31) <= LANES && col < a_.nt),
+    __device__ Stream(const StreamArgs& a_, const CUtensorMap* tm, unsigned char* s, int col)
+        : a(a_), tmap(tm), smem(s), i(col), own((threadIdx.x & 31) >= 1 && (threadIdx.x & 31) <= LANES && col < a_.nt),
           first_col(col == 0), last_col(col == a_.nt - 1) {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        rd = smem + a.in_off + warp * a.nr * WSLOT + 24 * lane;
+        rd = smem + a.in_off + warp * a.ng * GBYTES + 24 * lane;
         bar0 = smem_u32(smem);
-        wbar = bar0 + 8 * warp * a.nr;
-        c_slot = 0; c_phase = 0; kcons = 0; p_slot = 0; issued = 0; k_total = 0; vr0 = 0;
-        // slot byte b of the warp <-> byte 24 * LANES * warp - 32 + b of the input row
+        wbar = bar0 + 8 * warp * a.ng;
+        c_g = 0; c_phase = 0; g_cons = 0; p_g = 0; g_issued = 0; g_total = 0; vg0 = 0; frame_row0 = 0;
+        // ring-row byte b of the warp <-> byte 24 * LANES * warp - 32 + b of the input row
         const int lo = 24 * LANES * warp - 32;
+        box_x = lo / 4;                                   // (uint32 elements; negative = zero-filled by the TMA unit)
         src_off = max(lo, 0);
         dst_off = src_off - lo;
         cp_bytes = min(a.rowbytes, lo + WSLOT) - src_off;
         dn = 0; seg_n0 = 0; seg_q0 = 0;
+        duty_m = 0; turn_w = 0; turn_c = 0;
     }
     __device__ __forceinline__ DutyState* duty_state() const { return reinterpret_cast<DutyState*>(smem + a.duty_off); }
     __device__ __forceinline__ void wait_row(int n) { mbar_wait(bar0 + a.rbar_off + 8 * (n & (RS - 1)), (uint32_t)((n / RS) & 1)); }
     __device__ __forceinline__ void wait_duty(int n) { mbar_wait(bar0 + a.rbar_off + 8 * (RS + (n & (RS - 1))), (uint32_t)((n / RS) & 1)); }
 
     // ---- the warp's input ring ------------------------------------------------------------------
-    // Every row the warp has consumed so far (kcons) has been read by all its lanes: lane 0
-    // requests the next rows into those slots.
+    // Group G of a segment = virtual input rows vg0 + 2G, vg0 + 2G + 1 (reflect-101 at the frame's
+    // top / bottom).  Inside the frame the two rows are one TMA box (cp.async.bulk.tensor.2d on a
+    // (T*H) x (3W/4) uint32 view of the clip; columns outside the row are zero-filled); at the
+    // frame's edges they are two plain bulk copies.
+    __device__ __forceinline__ void issue_group(int G) {
+        const int v = vg0 + 2 * G;
+        const uint32_t bar = wbar + 8 * p_g;
+        const uint32_t dst = smem_u32(rd) + p_g * GBYTES;
+        if (v >= 0 && v + 1 < a.H) {
+            mbar_expect_tx(bar, (uint32_t)GBYTES);
+            tensor_g2s(dst, tmap, box_x, frame_row0 + v, bar);
+        } else {
+            mbar_expect_tx(bar, 2u * (uint32_t)cp_bytes);
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+                bulk_g2s(dst + r * WSLOT + dst_off, frame + (size_t)vhr_reflect101(v + r, a.H) * a.rowbytes + src_off,
+                         (uint32_t)cp_bytes, bar);
+        }
+        p_g = (p_g + 1 == a.ng) ? 0 : p_g + 1;
+    }
+    // Every group the warp has consumed so far has been read by all its lanes: lane 0 requests the
+    // next groups into those slots.
     __device__ __forceinline__ void refill() {
         __syncwarp();
         if ((threadIdx.x & 31) == 0) {
-            const int lim = min(k_total, kcons + a.nr);
-            while (issued < lim) {
-                const int row = vhr_reflect101(vr0 + issued, a.H);
-                const uint32_t bar = wbar + 8 * p_slot;
-                mbar_expect_tx(bar, (uint32_t)cp_bytes);
-                bulk_g2s(smem_u32(rd) + p_slot * WSLOT + dst_off, frame + (size_t)row * a.rowbytes + src_off, (uint32_t)cp_bytes, bar);
-                p_slot = (p_slot + 1 == a.nr) ? 0 : p_slot + 1;
-                ++issued;
-            }
+            const int lim = min(g_total, g_cons + a.ng);
+            while (g_issued < lim) issue_group(g_issued++);
         }
     }
-    // Next input row of the segment -> its level-1 horizontal pass (6 packed registers).
-    __device__ __forceinline__ void consume(uint32_t (&hp)[6]) {
-        mbar_wait(wbar + 8 * c_slot, (uint32_t)c_phase);
-        const unsigned char* p = rd + c_slot * WSLOT;
+    // level-1 horizontal pass of one ring row (6 packed registers)
+    __device__ __forceinline__ void hrow(const unsigned char* p, uint32_t (&hp)[6]) {
         uint32_t wd[9];
         const uint2 q0 = *reinterpret_cast<const uint2*>(p), q1 = *reinterpret_cast<const uint2*>(p + 8);
         const uint2 q2 = *reinterpret_cast<const uint2*>(p + 16), q3 = *reinterpret_cast<const uint2*>(p + 24);
@@ -219,25 +241,28 @@ struct Stream {
         }
         if (last_col) wd[8] = __byte_perm(wd[6], wd[7], 0x0432);   // pixel W reflects to W-2
         HPass<0>::run(wd, hp);
-        ++kcons;
-        if (++c_slot == a.nr) { c_slot = 0; c_phase ^= 1; }
+    }
+    // Next group of the segment -> the level-1 horizontal passes of its two rows.
+    template <bool FIRST>
+    __device__ __forceinline__ void consume(uint32_t (&ha)[6], uint32_t (&hb)[6]) {
+        mbar_wait(wbar + 8 * c_g, (uint32_t)c_phase);
+        const unsigned char* p = rd + c_g * GBYTES;
+        if constexpr (!FIRST) hrow(p, ha);              // (the first row of a segment's group 0 is a filler)
+        hrow(p + WSLOT, hb);
+        ++g_cons;
+        if (++c_g == a.ng) { c_g = 0; c_phase ^= 1; }
     }
 
     // ---- level 1: one row = two new input rows + the packed vertical pass ---------------------
     __device__ __forceinline__ void prime() {       // first three input rows of a segment
-#pragma unroll 1
-        for (int p = 0; p < 3; ++p) {
-            uint32_t hn[6];
-            consume(hn);
-#pragma unroll
-            for (int k = 0; k < 6; ++k) { w0[k] = w1[k]; w1[k] = w2[k]; w2[k] = hn[k]; }
-        }
+        uint32_t filler[6];
+        consume<true>(filler, w0);
+        consume<false>(w1, w2);
         refill();
     }
     __device__ __forceinline__ void l1_row(uint32_t (&v)[6]) {
         uint32_t w3[6], w4[6];
-        consume(w3);
-        consume(w4);
+        consume<false>(w3, w4);
 #pragma unroll
         for (int k = 0; k < 6; ++k) {      // packed 16-bit lanes (max 65280: no carry between halves)
             v[k] = (w0[k] + w4[k]) + ((w1[k] + w3[k]) << 2) + w2[k] * 6u;
@@ -280,11 +305,12 @@ struct Stream {
         }
         nextr[1] = seg_next[1]; lastr[1] = seg_last[1];
         if constexpr (L >= 2) { nextr[2] = seg_next[2]; lastr[2] = seg_last[2]; }
-        // input rows of the segment: virtual rows 2*first-2 .. 2*last+2 (reflected by the producer)
-        vr0 = 2 * nextr[1] - 2;
-        k_total = 2 * (lastr[1] - nextr[1] + 1) + 3;
-        issued = 0;
-        kcons = 0;
+        // input rows of the segment: virtual rows 2*first-2 .. 2*last+2 in groups of two, after one filler row
+        vg0 = 2 * nextr[1] - 3;
+        g_total = (lastr[1] - nextr[1] + 1) + 2;
+        g_issued = 0;
+        g_cons = 0;
+        frame_row0 = t * a.H;
         seg_n0 = dn;
         seg_q0 = (L >= 2) ? nextr[L >= 2 ? 2 : 1] : 0;
     }
@@ -393,27 +419,30 @@ struct Stream {
             f[k] = (float)s * (1.0f / 65536.0f);
         }
     }
-    // The warp whose turn it is for level-2 row q (turns rotate so that the heavier rows, which
-    // also finish rows of the upper levels, do not always fall on the same warps).
-    __device__ __forceinline__ bool my_turn(int q) const {
-        const int nw = blockDim.x >> 5;
-        return (q + q / nw) % nw == (int)(threadIdx.x >> 5);
-    }
-    // Upper levels of level-2 row number n of this segment, by the warp whose turn it is: the row
-    // must be complete and the previous row's upper-level work done (shared H rings, DutyState).
+    // Upper levels of the next level-2 row (number duty_m), by the warp whose turn it is.  Turns
+    // rotate with a skew (warp (n + n / nw) % nw) so that the heavier rows, which also finish rows
+    // of the upper levels, do not always fall on the same warps.  The row must be complete and the
+    // previous row's upper-level work done (shared H rings, DutyState).
     // Every parity wait below lags its barrier by less than one phase: the next phase of row
     // barrier n % RS needs this warp's signal for row n + RS, which follows duty(n) in program
     // order via the slot wait in publish(); the next phase of duty barrier (n-1) % RS needs duty(n).
-    __device__ __forceinline__ void run_duty(int n) {
+    __device__ __forceinline__ void run_duty() {
         if constexpr (L >= 3) {
-            const int q = seg_q0 + (n - seg_n0);
-            if (!my_turn(q)) return;
-            wait_row(n);
-            if (n >= 1) wait_duty(n - 1);
-            duty_row<3>(q, n & (RS - 1));
-            __syncwarp();
-            if ((threadIdx.x & 31) == 0)
-                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar0 + a.rbar_off + 8 * (RS + (n & (RS - 1)))) : "memory");
+            const int n = duty_m;
+            if (turn_w == (int)(threadIdx.x >> 5)) {
+                wait_row(n);
+                if (n >= 1) wait_duty(n - 1);
+                duty_row<3>(seg_q0 + (n - seg_n0), n & (RS - 1));
+                __syncwarp();
+                if ((threadIdx.x & 31) == 0)
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar0 + a.rbar_off + 8 * (RS + (n & (RS - 1)))) : "memory");
+            }
+            const int nw = blockDim.x >> 5;
+            duty_m = n + 1;
+            ++turn_w;
+            if (++turn_c == nw) { turn_c = 0; ++turn_w; }
+            if (turn_w >= nw) turn_w -= nw;
+            if (turn_w >= nw) turn_w -= nw;
         }
     }
     __device__ __forceinline__ void publish(int q, const float (&f)[6]) {
@@ -452,7 +481,7 @@ struct Stream {
         }
         dn = n + 1;
         nextr[2] = q + 1;
-        if (n - DLY >= seg_n0) run_duty(n - DLY);    // an older row: complete by now, and nobody waits for its upper levels yet
+        if (n - DLY >= seg_n0) run_duty();           // an older row: complete by now, and nobody waits for its upper levels yet
     }
 
     // ---- one segment ----------------------------------------------------------------------------
@@ -528,20 +557,20 @@ struct Stream {
                 refill();
                 publish(q, f);
             }
-            for (int n = max(dn - DLY, seg_n0); n < dn; ++n) run_duty(n);    // the last rows of the segment
+            while (duty_m < dn) run_duty();          // the last rows of the segment
         }
     }
 };
 
 template <int L, int MAXT>
-__global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) pyrdown_stream_kernel(const StreamArgs a) {
-    extern __shared__ __align__(16) unsigned char smem[];
+__global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) pyrdown_stream_kernel(const StreamArgs a, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(128) unsigned char smem[];
     const long long lo = a.total_rows * blockIdx.x / gridDim.x;
     const long long hi = a.total_rows * (blockIdx.x + 1) / gridDim.x;
     if (lo >= hi) return;
     if (threadIdx.x == 0) {
         const int nw = blockDim.x >> 5;
-        for (int b = 0; b < nw * a.nr; ++b) mbar_init(smem_u32(smem) + 8 * b, 1);             // rows landed, per warp and slot
+        for (int b = 0; b < nw * a.ng; ++b) mbar_init(smem_u32(smem) + 8 * b, 1);             // rows landed, per warp and group
         for (int b = 0; b < RS; ++b) {
             mbar_init(smem_u32(smem) + a.rbar_off + 8 * b, nw);                                // row barriers: one arrival per warp
             mbar_init(smem_u32(smem) + a.rbar_off + 8 * (RS + b), 1);                          // duty barriers: one arrival per row
@@ -551,7 +580,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) pyrdown_stream_kern
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     const int col = (int)(threadIdx.x >> 5) * LANES + (int)(threadIdx.x & 31) - 1;
-    Stream<L> st(a, smem, col);
+    Stream<L> st(a, &tmap, smem, col);
     const int hL = a.h[L];
     long long pos = lo;
     while (pos < hi) {
@@ -566,7 +595,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) pyrdown_stream_kern
 }
 
 template <int L, int MAXT>
-int launch_stream(vhr_ctx* ctx, const StreamArgs& a, int threads, int smem_bytes, cudaStream_t stream) {
+int launch_stream(vhr_ctx* ctx, const StreamArgs& a, const CUtensorMap& tmap, int threads, int smem_bytes, cudaStream_t stream) {
     auto kern = pyrdown_stream_kernel<L, MAXT>;
     VHR_CHECK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     int per_sm = 0;
@@ -574,19 +603,19 @@ int launch_stream(vhr_ctx* ctx, const StreamArgs& a, int threads, int smem_bytes
     if (per_sm < 1) return VHR_ERR_UNSUPPORTED;
     long long grid = (long long)per_sm * ctx->num_sms;
     if (grid > a.total_rows) grid = a.total_rows;
-    kern<<<(int)grid, threads, smem_bytes, stream>>>(a);
+    kern<<<(int)grid, threads, smem_bytes, stream>>>(a, tmap);
     return vhr_after_launch(ctx, "pyrdown_stream_kernel");
 }
 
 template <int MAXT>
-int dispatch_stream(vhr_ctx* ctx, const StreamArgs& a, int threads, int smem_bytes, cudaStream_t stream) {
+int dispatch_stream(vhr_ctx* ctx, const StreamArgs& a, const CUtensorMap& tmap, int threads, int smem_bytes, cudaStream_t stream) {
     switch (a.levels) {
-        case 1: return launch_stream<1, MAXT>(ctx, a, threads, smem_bytes, stream);
-        case 2: return launch_stream<2, MAXT>(ctx, a, threads, smem_bytes, stream);
-        case 3: return launch_stream<3, MAXT>(ctx, a, threads, smem_bytes, stream);
-        case 4: return launch_stream<4, MAXT>(ctx, a, threads, smem_bytes, stream);
-        case 5: return launch_stream<5, MAXT>(ctx, a, threads, smem_bytes, stream);
-        case 6: return launch_stream<6, MAXT>(ctx, a, threads, smem_bytes, stream);
+        case 1: return launch_stream<1, MAXT>(ctx, a, tmap, threads, smem_bytes, stream);
+        case 2: return launch_stream<2, MAXT>(ctx, a, tmap, threads, smem_bytes, stream);
+        case 3: return launch_stream<3, MAXT>(ctx, a, tmap, threads, smem_bytes, stream);
+        case 4: return launch_stream<4, MAXT>(ctx, a, tmap, threads, smem_bytes, stream);
+        case 5: return launch_stream<5, MAXT>(ctx, a, tmap, threads, smem_bytes, stream);
+        case 6: return launch_stream<6, MAXT>(ctx, a, tmap, threads, smem_bytes, stream);
     }
     return VHR_ERR_INVALID;
 }
@@ -618,18 +647,19 @@ int vhr_pyrdown_stream(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int 
         fixed = al16(fixed + (l == 2 ? RS : 2) * 3 * a.ring_stride[l] * 4);
     }
     for (int l = 3; l <= levels; ++l) fixed = al16(fixed + HR * 3 * a.w[l] * 4);
-    // per-warp input rings: as deep as two CTAs per SM allow (at most 4 rows are consumed between two refills)
+    // per-warp input rings: as deep as two CTAs per SM allow (2 groups are consumed between two refills)
     const int budget = (threads <= 256 ? ctx->smem_optin / 2 - 2048 : ctx->smem_optin - 1024);
-    int nr = 12;
-    auto head = [&](int n) { return al16(8 * (warps * n + 2 * RS)) + al16((int)sizeof(DutyState)); };
-    while (nr > 6 && head(nr) + warps * nr * WSLOT + fixed > budget) --nr;
-    if (head(nr) + warps * nr * WSLOT + fixed > ctx->smem_optin) return VHR_ERR_UNSUPPORTED;
-    a.nr = nr;
-    a.rbar_off = 8 * warps * nr;
-    a.duty_off = al16(8 * (warps * nr + 2 * RS));
-    int off = head(nr);
+    int ng = 6;
+    auto al128 = [](int v) { return (v + 127) & ~127; };
+    auto head = [&](int n) { return al128(al16(8 * (warps * n + 2 * RS)) + al16((int)sizeof(DutyState))); };
+    while (ng > 3 && head(ng) + warps * ng * GBYTES + fixed > budget) --ng;
+    if (head(ng) + warps * ng * GBYTES + fixed > ctx->smem_optin) return VHR_ERR_UNSUPPORTED;
+    a.ng = ng;
+    a.rbar_off = 8 * warps * ng;
+    a.duty_off = al16(8 * (warps * ng + 2 * RS));
+    int off = head(ng);
     a.in_off = off;
-    off = al16(off + warps * nr * WSLOT);
+    off = al16(off + warps * ng * GBYTES);
     for (int l = 2; l < levels; ++l) {
         a.ring_off[l] = off;
         off = al16(off + (l == 2 ? RS : 2) * 3 * a.ring_stride[l] * 4);
@@ -638,6 +668,26 @@ int vhr_pyrdown_stream(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int 
         a.hring_off[l] = off;
         off = al16(off + HR * 3 * a.w[l] * 4);
     }
-    if (threads <= 256) return dispatch_stream<256>(ctx, a, threads, off, stream);
-    return dispatch_stream<512>(ctx, a, threads, off, stream);
+    // the clip as a 2-D uint32 tensor: (T*H) rows x (3W/4) elements; box = one warp's two-row group
+    static PFN_cuTensorMapEncodeTiled encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+            cudaGetLastError();
+            return VHR_ERR_UNSUPPORTED;
+        }
+        encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+    }
+    CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {(cuuint64_t)(a.rowbytes / 4), (cuuint64_t)T * (cuuint64_t)H};
+    const cuuint64_t gstr[1] = {(cuuint64_t)a.rowbytes};
+    const cuuint32_t box[2] = {WSLOT / 4, 2};
+    const cuuint32_t estr[2] = {1, 1};
+    if (encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint8_t*>(d_frames), gdim, gstr, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return VHR_ERR_UNSUPPORTED;
+    if (threads <= 256) return dispatch_stream<256>(ctx, a, tmap, threads, off, stream);
+    return dispatch_stream<512>(ctx, a, tmap, threads, off, stream);
 }
