@@ -51,6 +51,16 @@ def pulse_hz(clip: int) -> float:
     return 0.8 + (clip % 64) * (2.4 / 63.0)
 
 
+def recorded_traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/r1_traffic.json);
+    None when there is no record for this workload."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[kernel]
+        return int(rec["traffic_bytes"])
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -337,8 +347,11 @@ def run_gpu(args):
                            "frames_per_step_per_gpu": T, "resident_clips_per_gpu": n_res, "roi": "1 cheek rectangle",
                            "bpm": "whole-clip window, float32 detrend + FFT peak",
                            "l2": "inputs (11.2 GB/clip at 1080p) larger than L2; no flush", "parallelism": f"clip-sharded x{world}"},
-                "roofline": {"bound": "hbm", "kernel": "collapse_kernel", "achieved": achieved, "peak": peak_gbs,
-                             "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                "roofline": {"bound": "hbm", "kernel": "collapse_sep_kernel", "achieved": achieved, "peak": peak_gbs,
+                             "unit": "GB/s", "frac": achieved / peak_gbs,
+                             "traffic": recorded_traffic("collapse_sep_kernel") if args.workload == "c4" else None,
+                             "traffic_source": "ncu --set full capture of the same command, profiles/r1_traffic.json",
+                             "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": collapse_bytes_per_frame * T, "ms_per_launch": col_ms},
                 "path_roofline": {"stages": "pyrdown+bandpass+collapse", "bytes_per_frame": bytes_per_frame,
                                   "achieved": path_achieved, "frac": path_achieved / peak_gbs, "unit": "GB/s"},
