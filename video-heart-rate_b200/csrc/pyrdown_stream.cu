@@ -163,7 +163,9 @@ struct Stream {
     uint32_t wbar;            // shared address of the warp's group-0 "rows landed" barrier
     // the warp's input ring: consumer side (all lanes) and producer side (lane 0); unit = group of two rows
     int c_g, c_phase, g_cons;
-    int p_g, g_issued, g_total, vg0, frame_row0;
+    int p_g, g_issued, g_total, vg0;
+    int g_int0, g_int1, box_y0;                   // groups [g_int0, g_int1) lie inside the frame: one TMA box at row box_y0 + 2 G
+    uint32_t ring_u32;                            // shared address of the warp's input ring
     int src_off, cp_bytes, dst_off, box_x;        // the warp's byte range of an input row
     // Rows of level 2 are numbered across segments (dn = rows published so far, the same in every
     // warp).  Row barrier n % RS, phase n / RS: every warp has written its part of row n.
@@ -183,7 +185,9 @@ struct Stream {
         rd = smem + a.in_off + warp * a.ng * GBYTES + 24 * lane;
         bar0 = smem_u32(smem);
         wbar = bar0 + 8 * warp * a.ng;
-        c_g = 0; c_phase = 0; g_cons = 0; p_g = 0; g_issued = 0; g_total = 0; vg0 = 0; frame_row0 = 0;
+        c_g = 0; c_phase = 0; g_cons = 0; p_g = 0; g_issued = 0; g_total = 0; vg0 = 0;
+        g_int0 = 0; g_int1 = 0; box_y0 = 0;
+        ring_u32 = smem_u32(smem + a.in_off + warp * a.ng * GBYTES);
         // ring-row byte b of the warp <-> byte 24 * LANES * warp - 32 + b of the input row
         const int lo = 24 * LANES * warp - 32;
         box_x = lo / 4;                                   // (uint32 elements; negative = zero-filled by the TMA unit)
@@ -203,13 +207,13 @@ struct Stream {
     // (T*H) x (3W/4) uint32 view of the clip; columns outside the row are zero-filled); at the
     // frame's edges they are two plain bulk copies.
     __device__ __forceinline__ void issue_group(int G) {
-        const int v = vg0 + 2 * G;
         const uint32_t bar = wbar + 8 * p_g;
-        const uint32_t dst = smem_u32(rd) + p_g * GBYTES;
-        if (v >= 0 && v + 1 < a.H) {
+        const uint32_t dst = ring_u32 + p_g * GBYTES;
+        if (G >= g_int0 && G < g_int1) {
             mbar_expect_tx(bar, (uint32_t)GBYTES);
-            tensor_g2s(dst, tmap, box_x, frame_row0 + v, bar);
+            tensor_g2s(dst, tmap, box_x, box_y0 + 2 * G, bar);
         } else {
+            const int v = vg0 + 2 * G;
             mbar_expect_tx(bar, 2u * (uint32_t)cp_bytes);
 #pragma unroll
             for (int r = 0; r < 2; ++r)
@@ -310,7 +314,9 @@ struct Stream {
         g_total = (lastr[1] - nextr[1] + 1) + 2;
         g_issued = 0;
         g_cons = 0;
-        frame_row0 = t * a.H;
+        g_int0 = vg0 < 0 ? (1 - vg0) / 2 : 0;                 // first G with vg0 + 2G >= 0
+        g_int1 = (a.H - vg0) / 2;                            // first G with vg0 + 2G + 1 >= H  (vg0 odd)
+        box_y0 = t * a.H + vg0;
         seg_n0 = dn;
         seg_q0 = (L >= 2) ? nextr[L >= 2 ? 2 : 1] : 0;
     }
