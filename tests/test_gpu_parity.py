@@ -94,6 +94,36 @@ def test_pyrdown_many_frames_persistent_split(vhr, eng):
     assert rel_err(got, oevm.pyrdown_cascade(fr, 4)) <= REL
 
 
+@pytest.mark.parametrize("case", [(400, 70, 128, 4), (300, 70, 128, 3), (2, 40, 3840, 4), (2, 33, 2048, 3),
+                                  (3, 200, 256, 5), (2, 130, 320, 6), (5, 1080, 1920, 4), (40, 36, 64, 2)])
+def test_pyrdown_stream_kernel(vhr, eng, case, monkeypatch):
+    """The streaming kernel (W % 64 == 0: registers + shuffles for levels 1-2, per-warp TMA input rings,
+    upper levels by one warp in turn) on shapes that exercise shares crossing frames, the 512-thread
+    variant (W > 1920), 5 and 6 levels, odd level heights; held to the oracle and to the previous fast
+    path (same arithmetic, block barriers)."""
+    import torch
+    T, H, W, levels = case
+    rng = np.random.default_rng(T + H + W + levels)
+    fr = rng.integers(0, 256, (T, H, W, 3), dtype=np.uint8)
+    frd = torch.as_tensor(fr, device=eng.tdev)
+    got = eng.pyrdown(frd, levels).cpu().numpy()
+    n_ref = min(T, 6)                                         # the oracle on the first and last frames
+    sel = np.r_[0:n_ref // 2, T - (n_ref - n_ref // 2):T]
+    ref = oevm.pyrdown_cascade(fr[sel], levels)
+    assert got.shape[1:] == ref.shape[1:]
+    if levels <= 2:
+        np.testing.assert_array_equal(got[sel], ref.astype(np.float32))
+    else:
+        assert rel_err(got[sel], ref) <= REL
+    monkeypatch.setenv("VHR_PYRDOWN_IMPL", "fast")
+    fast = eng.pyrdown(frd, levels).cpu().numpy()
+    monkeypatch.delenv("VHR_PYRDOWN_IMPL")
+    if levels <= 2:
+        np.testing.assert_array_equal(got, fast)
+    else:
+        assert rel_err(got, fast) <= 1e-6                     # every frame, every share boundary
+
+
 # --------------------------------------------------------------------------------- bandpass
 @pytest.mark.parametrize("case", [(150, 5.0, 432), (300, 30.0, 777), (299, 29.97, 64), (64, 10.0, 5), (1800, 30.0, 96)])
 def test_temporal_bandpass(vhr, eng, case):
