@@ -17,7 +17,7 @@
 
 namespace {
 
-constexpr int BT = 128;
+constexpr int BT = 256;
 constexpr int MAXSEC = 16;
 constexpr int MAXTAPS = 128;
 constexpr int MAXCOEF = (MAXSEC * 6 > MAXTAPS) ? MAXSEC * 6 : MAXTAPS;
@@ -32,26 +32,43 @@ __device__ __forceinline__ double np_freq(int k, int n, double fs) {
     return __dmul_rn((double)k, val);
 }
 
-// detrend a window in place (x: n float64 samples in shared memory); thread 0 only
+// detrend a window in place (x: n float64 samples in shared memory); called by every thread of the
+// block.  The element-wise steps are spread over the threads; each sum runs on thread 0 in
+// NumPy's pairwise order (the order decides the last bit of the mean, hence near-tie bins).
 __device__ void detrend_window(double* x, float* xf, int n, int mode) {
+    __shared__ double s_m;
+    __shared__ float s_mf;
+    const int tid = threadIdx.x, nt = blockDim.x;
     if (mode == VHR_DETREND_F64) {
         // np.mean(float64): pairwise sum / n  (rppg_VIDEO.py:399)
-        const double m = __ddiv_rn(pairwise_sum_f64(x, n), (double)n);
-        for (int i = 0; i < n; ++i) x[i] = __dsub_rn(x[i], m);
+        if (tid == 0) s_m = __ddiv_rn(pairwise_sum_f64(x, n), (double)n);
+        __syncthreads();
+        const double m = s_m;
+        for (int i = tid; i < n; i += nt) x[i] = __dsub_rn(x[i], m);
     } else if (mode == VHR_DETREND_F32) {
         // sig = float32(deque); sig - np.mean(sig): float32 pairwise mean (green_avg.py:42-43)
-        for (int i = 0; i < n; ++i) xf[i] = (float)x[i];
-        const float m = __fdiv_rn(pairwise_sum_f32(xf, n), (float)n);
-        for (int i = 0; i < n; ++i) x[i] = (double)__fsub_rn(xf[i], m);
+        for (int i = tid; i < n; i += nt) xf[i] = (float)x[i];
+        __syncthreads();
+        if (tid == 0) s_mf = __fdiv_rn(pairwise_sum_f32(xf, n), (float)n);
+        __syncthreads();
+        const float m = s_mf;
+        for (int i = tid; i < n; i += nt) x[i] = (double)__fsub_rn(xf[i], m);
     } else if (mode == VHR_DETREND_ZSCORE_F32) {
         // (sig - np.mean(sig)) / np.std(sig) on a float32 vector (green_avg_psd_plot.py:174-175):
         // np.std = sqrt(pairwise_sum((x - mean)^2) / n), every step in float32
-        for (int i = 0; i < n; ++i) xf[i] = (float)x[i];
-        const float m = __fdiv_rn(pairwise_sum_f32(xf, n), (float)n);
-        for (int i = 0; i < n; ++i) { const float d = __fsub_rn(xf[i], m); x[i] = (double)d; xf[i] = __fmul_rn(d, d); }
-        const float sd = __fsqrt_rn(__fdiv_rn(pairwise_sum_f32(xf, n), (float)n));
-        for (int i = 0; i < n; ++i) x[i] = (double)__fdiv_rn((float)x[i], sd);
+        for (int i = tid; i < n; i += nt) xf[i] = (float)x[i];
+        __syncthreads();
+        if (tid == 0) s_mf = __fdiv_rn(pairwise_sum_f32(xf, n), (float)n);
+        __syncthreads();
+        const float m = s_mf;
+        for (int i = tid; i < n; i += nt) { const float d = __fsub_rn(xf[i], m); x[i] = (double)d; xf[i] = __fmul_rn(d, d); }
+        __syncthreads();
+        if (tid == 0) s_mf = __fsqrt_rn(__fdiv_rn(pairwise_sum_f32(xf, n), (float)n));
+        __syncthreads();
+        const float sd = s_mf;
+        for (int i = tid; i < n; i += nt) x[i] = (double)__fdiv_rn((float)x[i], sd);
     }
+    __syncthreads();
 }
 
 // |X_k|^2 of x[0..n) (float64), twiddles from a table tw[m] = (cos, sin)(2 pi m / n)
@@ -153,8 +170,7 @@ __global__ void __launch_bounds__(BT) bpm_fft_kernel(const FftArgs a) {
         __syncthreads();
         for (int i = threadIdx.x; i < n; i += BT) x[i] = a.trace[(size_t)(s + i) * a.C + c];
         __syncthreads();
-        if (threadIdx.x == 0) detrend_window(x, xf, n, a.detrend);
-        __syncthreads();
+        detrend_window(x, xf, n, a.detrend);
         ArgMax mine;
         mine.v = 0.;
         mine.k = -1;
@@ -257,8 +273,7 @@ __global__ void __launch_bounds__(BT) bpm_welch_kernel(const __grid_constant__ W
     }
     for (int i = threadIdx.x; i < n; i += BT) x[i] = a.trace[s + i];
     __syncthreads();
-    if (threadIdx.x == 0) detrend_window(x, xf, n, a.detrend);
-    __syncthreads();
+    detrend_window(x, xf, n, a.detrend);
 
     const int ne = n + 2 * edge;
     if (a.filt_kind != VHR_FILT_NONE) {
