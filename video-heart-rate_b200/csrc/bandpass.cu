@@ -159,9 +159,81 @@ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(
 template <bool INV>
 __device__ __forceinline__ float2 mul_mi(float2 a) { return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x); }
 
+// exp(+2 pi i m / N) for the inner twiddles of the composite radices (m is a compile-time constant
+// after unrolling, so the switch folds to two literals)
+template <int N>
+__device__ __forceinline__ float2 unit_root(int m) {
+    if constexpr (N == 8) {
+        switch (m) {
+        case 0: return make_float2(1.000000000e+00f, 0.000000000e+00f);
+        case 1: return make_float2(7.071067812e-01f, 7.071067812e-01f);
+        case 2: return make_float2(0.0f, 1.000000000e+00f);
+        case 3: return make_float2(-7.071067812e-01f, 7.071067812e-01f);
+        case 4: return make_float2(-1.000000000e+00f, 0.0f);
+        case 5: return make_float2(-7.071067812e-01f, -7.071067812e-01f);
+        case 6: return make_float2(0.0f, -1.000000000e+00f);
+        case 7: return make_float2(7.071067812e-01f, -7.071067812e-01f);
+        }
+    }
+    if constexpr (N == 9) {
+        switch (m) {
+        case 0: return make_float2(1.000000000e+00f, 0.000000000e+00f);
+        case 1: return make_float2(7.660444431e-01f, 6.427876097e-01f);
+        case 2: return make_float2(1.736481777e-01f, 9.848077530e-01f);
+        case 3: return make_float2(-5.000000000e-01f, 8.660254038e-01f);
+        case 4: return make_float2(-9.396926208e-01f, 3.420201433e-01f);
+        case 5: return make_float2(-9.396926208e-01f, -3.420201433e-01f);
+        case 6: return make_float2(-5.000000000e-01f, -8.660254038e-01f);
+        case 7: return make_float2(1.736481777e-01f, -9.848077530e-01f);
+        case 8: return make_float2(7.660444431e-01f, -6.427876097e-01f);
+        }
+    }
+    static_assert(N == 8 || N == 9, "unit_root");
+    return make_float2(1.0f, 0.0f);
+}
+
+template <int R, bool INV>
+__device__ __forceinline__ void dft_small(float2 (&v)[R]);
+
+// DFT of size R1*R2 in natural order, in registers: n = R2 n1 + n2, k = k1 + R1 k2;
+// R1-point DFTs over n1, inner twiddles W_N^(n2 k1), R2-point DFTs over n2
+template <int R1, int R2, bool INV>
+__device__ __forceinline__ void dft_comp(float2 (&v)[R1 * R2]) {
+    float2 A[R2][R1];
+#pragma unroll
+    for (int n2 = 0; n2 < R2; ++n2) {
+        float2 u[R1];
+#pragma unroll
+        for (int n1 = 0; n1 < R1; ++n1) u[n1] = v[R2 * n1 + n2];
+        dft_small<R1, INV>(u);
+#pragma unroll
+        for (int k1 = 0; k1 < R1; ++k1) {
+            if (n2 * k1 != 0) {
+                const float2 w = unit_root<R1 * R2>((n2 * k1) % (R1 * R2));
+                A[n2][k1] = cmul(u[k1], make_float2(w.x, INV ? w.y : -w.y));
+            } else {
+                A[n2][k1] = u[k1];
+            }
+        }
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < R1; ++k1) {
+        float2 t[R2];
+#pragma unroll
+        for (int n2 = 0; n2 < R2; ++n2) t[n2] = A[n2][k1];
+        dft_small<R2, INV>(t);
+#pragma unroll
+        for (int k2 = 0; k2 < R2; ++k2) v[k1 + R1 * k2] = t[k2];
+    }
+}
+
 template <int R, bool INV>
 __device__ __forceinline__ void dft_small(float2 (&v)[R]) {
-    if constexpr (R == 2) {
+    if constexpr (R == 8) {
+        dft_comp<4, 2, INV>(v);
+    } else if constexpr (R == 9) {
+        dft_comp<3, 3, INV>(v);
+    } else if constexpr (R == 2) {
         const float2 a = v[0], b = v[1];
         v[0] = cadd(a, b); v[1] = csub(a, b);
     } else if constexpr (R == 3) {
@@ -224,9 +296,41 @@ __device__ __forceinline__ void fft_pass(float2* __restrict__ z, const float2* _
     }
 }
 
+// the same pass for the composite radices (8, 9): one work item = one butterfly of one series
+// (the R - 1 outer twiddles no longer fit in registers beside the R values, and T / R butterflies
+// alone would leave most of the block idle)
+template <int R, bool INV>
+__device__ __forceinline__ void fft_pass_big(float2* __restrict__ z, const float2* __restrict__ tws, int T, int n,
+                                             unsigned inv_m) {
+    const int m = n / R, step = T / n, nb = T / R;
+    for (int it = threadIdx.x; it < nb * FG; it += FT) {
+        const int s = it / nb, b = it - s * nb;
+        const int block = inv_m ? (int)__umulhi((unsigned)b, inv_m) : b;     // inv_m == 0 encodes m == 1
+        const int j = b - block * m;
+        float2* zs = z + (size_t)s * T + block * n + j;
+        const int js = j * step;
+        float2 v[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) v[q] = zs[q * m];
+        if (INV && js != 0) {
+#pragma unroll
+            for (int q = 1; q < R; ++q) v[q] = cmul(v[q], tws[js * q]);
+        }
+        dft_small<R, INV>(v);
+        if (!INV && js != 0) {
+#pragma unroll
+            for (int q = 1; q < R; ++q) { const float2 t = tws[js * q]; v[q] = cmul(v[q], make_float2(t.x, -t.y)); }
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) zs[q * m] = v[q];
+    }
+}
+
 template <bool INV>
 __device__ __forceinline__ void fft_dispatch(float2* z, const float2* tws, int T, int r, int n, unsigned inv_m) {
     switch (r) {
+        case 9: fft_pass_big<9, INV>(z, tws, T, n, inv_m); break;
+        case 8: fft_pass_big<8, INV>(z, tws, T, n, inv_m); break;
         case 5: fft_pass<5, INV>(z, tws, T, n, inv_m); break;
         case 3: fft_pass<3, INV>(z, tws, T, n, inv_m); break;
         case 4: fft_pass<4, INV>(z, tws, T, n, inv_m); break;
@@ -330,7 +434,9 @@ extern "C" int vhr_temporal_bandpass(vhr_ctx* ctx, const float* d_in, float* d_o
         const char* force = getenv("VHR_BANDPASS_DFT");          // test hook: exercise form (2)
         std::vector<int> radices;
         int n = T;
-        for (int f : {5, 3}) while (n % f == 0) { radices.push_back(f); n /= f; }
+        // composite radices first (9 = 3x3, 8 = 4x2 in registers): fewer shared-memory passes.  (25 = 5x5 was
+        // tried: 128 registers, 2 CTAs/SM and T/25 butterflies per series made the kernel 40 % slower.)
+        for (int f : {9, 8, 5, 3}) while (n % f == 0) { radices.push_back(f); n /= f; }
         while (n % 4 == 0) { radices.push_back(4); n /= 4; }
         while (n % 2 == 0) { radices.push_back(2); n /= 2; }
         const size_t smem_fft = (size_t)T * 8 * (FG + 1);
