@@ -263,7 +263,7 @@ __device__ __forceinline__ void dft_small(float2 (&v)[R]) {
 // butterfly, DIT (inverse) conjugate twiddles before it
 template <int R, bool INV>
 __device__ __forceinline__ void fft_pass(float2* __restrict__ z, const float2* __restrict__ tws, int T, int n,
-                                         unsigned inv_m) {
+                                         unsigned inv_m, const float* __restrict__ mask) {
     const int m = n / R, step = T / n, nb = T / R;
     for (int b = threadIdx.x; b < nb; b += FT) {
         const int block = inv_m ? (int)__umulhi((unsigned)b, inv_m) : b;     // inv_m == 0 encodes m == 1
@@ -290,6 +290,10 @@ __device__ __forceinline__ void fft_pass(float2* __restrict__ z, const float2* _
 #pragma unroll
                 for (int q = 1; q < R; ++q) v[q] = cmul(v[q], w[q]);
             }
+            if (mask) {          // last forward pass: the band mask (gain / T on kept bins) rides on the store
+#pragma unroll
+                for (int q = 0; q < R; ++q) { const float mk = __ldg(mask + base + q * m); v[q] = make_float2(v[q].x * mk, v[q].y * mk); }
+            }
 #pragma unroll
             for (int q = 0; q < R; ++q) zs[q * m] = v[q];
         }
@@ -301,13 +305,14 @@ __device__ __forceinline__ void fft_pass(float2* __restrict__ z, const float2* _
 // alone would leave most of the block idle)
 template <int R, bool INV>
 __device__ __forceinline__ void fft_pass_big(float2* __restrict__ z, const float2* __restrict__ tws, int T, int n,
-                                             unsigned inv_m) {
+                                             unsigned inv_m, const float* __restrict__ mask) {
     const int m = n / R, step = T / n, nb = T / R;
     for (int it = threadIdx.x; it < nb * FG; it += FT) {
         const int s = it / nb, b = it - s * nb;
         const int block = inv_m ? (int)__umulhi((unsigned)b, inv_m) : b;     // inv_m == 0 encodes m == 1
         const int j = b - block * m;
-        float2* zs = z + (size_t)s * T + block * n + j;
+        const int base = block * n + j;
+        float2* zs = z + (size_t)s * T + base;
         const int js = j * step;
         float2 v[R];
 #pragma unroll
@@ -321,20 +326,25 @@ __device__ __forceinline__ void fft_pass_big(float2* __restrict__ z, const float
 #pragma unroll
             for (int q = 1; q < R; ++q) { const float2 t = tws[js * q]; v[q] = cmul(v[q], make_float2(t.x, -t.y)); }
         }
+        if (mask) {
+#pragma unroll
+            for (int q = 0; q < R; ++q) { const float mk = __ldg(mask + base + q * m); v[q] = make_float2(v[q].x * mk, v[q].y * mk); }
+        }
 #pragma unroll
         for (int q = 0; q < R; ++q) zs[q * m] = v[q];
     }
 }
 
 template <bool INV>
-__device__ __forceinline__ void fft_dispatch(float2* z, const float2* tws, int T, int r, int n, unsigned inv_m) {
+__device__ __forceinline__ void fft_dispatch(float2* z, const float2* tws, int T, int r, int n, unsigned inv_m,
+                                             const float* mask) {
     switch (r) {
-        case 9: fft_pass_big<9, INV>(z, tws, T, n, inv_m); break;
-        case 8: fft_pass_big<8, INV>(z, tws, T, n, inv_m); break;
-        case 5: fft_pass<5, INV>(z, tws, T, n, inv_m); break;
-        case 3: fft_pass<3, INV>(z, tws, T, n, inv_m); break;
-        case 4: fft_pass<4, INV>(z, tws, T, n, inv_m); break;
-        default: fft_pass<2, INV>(z, tws, T, n, inv_m); break;
+        case 9: fft_pass_big<9, INV>(z, tws, T, n, inv_m, mask); break;
+        case 8: fft_pass_big<8, INV>(z, tws, T, n, inv_m, mask); break;
+        case 5: fft_pass<5, INV>(z, tws, T, n, inv_m, mask); break;
+        case 3: fft_pass<3, INV>(z, tws, T, n, inv_m, mask); break;
+        case 4: fft_pass<4, INV>(z, tws, T, n, inv_m, mask); break;
+        default: fft_pass<2, INV>(z, tws, T, n, inv_m, mask); break;
     }
 }
 
@@ -365,18 +375,11 @@ __global__ void __launch_bounds__(FT) bandpass_fft_kernel(const __grid_constant_
     }
     __syncthreads();
     for (int ps = 0; ps < a.npass; ++ps) {
-        fft_dispatch<false>(z, tws, T, a.radix[ps], a.sub[ps], a.inv_m[ps]);
+        fft_dispatch<false>(z, tws, T, a.radix[ps], a.sub[ps], a.inv_m[ps], ps == a.npass - 1 ? a.mask : nullptr);
         __syncthreads();
     }
-    for (int idx = threadIdx.x; idx < T * FG; idx += FT) {
-        const int s = idx / T, pos = idx - s * T;
-        const float mk = __ldg(a.mask + pos);
-        float2 v = z[idx];
-        z[idx] = make_float2(v.x * mk, v.y * mk);
-    }
-    __syncthreads();
     for (int ps = a.npass - 1; ps >= 0; --ps) {
-        fft_dispatch<true>(z, tws, T, a.radix[ps], a.sub[ps], a.inv_m[ps]);
+        fft_dispatch<true>(z, tws, T, a.radix[ps], a.sub[ps], a.inv_m[ps], nullptr);
         __syncthreads();
     }
     {
