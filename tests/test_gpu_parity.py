@@ -267,6 +267,52 @@ def test_poly_mask_and_means(vhr, eng):
                 assert np.isnan(m32[t, k].cpu().numpy()).all()
 
 
+@pytest.mark.parametrize("shape", [(64, 96), (40, 2300), (300, 520)])
+def test_poly_scanline_equals_per_pixel(vhr, eng, shape, monkeypatch):
+    """The scanline rasteriser (toggle bits + prefix-XOR per row) and the per-pixel form of the frozen rule
+    give the same pixel sets: random simple, self-intersecting and degenerate polygons, horizontal edges,
+    repeated vertices, vertices outside the frame, rows wider than 2048 pixels."""
+    import torch
+    H, W = shape
+    rng = np.random.default_rng(H * 7 + W)
+    T, K, V = 6, 5, 16
+    polys = np.zeros((T, K, V, 2), dtype=np.int32)
+    nv = np.zeros((T, K), dtype=np.int32)
+    for t in range(T):
+        for k in range(K):
+            n = int(rng.integers(3, V + 1))
+            if k == 0:                                            # random vertex order: self-intersecting
+                pts = np.stack([rng.integers(-20, W + 20, n), rng.integers(-10, H + 10, n)], 1)
+            elif k == 1:                                          # axis-aligned pieces: horizontal / vertical edges
+                xs = np.sort(rng.integers(0, W, 4)); ys = np.sort(rng.integers(0, H, 4))
+                pts = np.array([[xs[0], ys[0]], [xs[3], ys[0]], [xs[3], ys[2]], [xs[2], ys[2]], [xs[2], ys[3]], [xs[0], ys[3]]])
+                n = 6
+            elif k == 2:                                          # repeated vertices and collinear runs
+                base = np.stack([rng.integers(0, W, 4), rng.integers(0, H, 4)], 1)
+                pts = np.repeat(base, 2, axis=0)
+                n = 8
+            elif k == 3:                                          # star around the centre, partly off-frame
+                ang = np.sort(rng.uniform(0, 2 * np.pi, n))
+                r = rng.uniform(0.1, 0.8, n) * max(H, W) / 2
+                r[::2] *= 0.4
+                pts = np.stack([W / 2 + r * np.cos(ang), H / 2 + r * np.sin(ang)], 1)
+            else:                                                 # empty / point / segment
+                n = int(rng.integers(0, 3))
+                pts = np.stack([rng.integers(0, W, n), rng.integers(0, H, n)], 1) if n else np.zeros((0, 2))
+            polys[t, k, :n] = np.asarray(pts, dtype=np.int64).astype(np.int32)[:n]
+            nv[t, k] = n
+    fr8 = torch.as_tensor(rng.integers(0, 256, (T, H, W, 3), dtype=np.uint8), device=eng.tdev)
+    m_scan, c_scan = eng.roi_mean_poly(fr8, polys, nv)
+    monkeypatch.setenv("VHR_POLY_PIXEL", "1")
+    m_pix, c_pix = eng.roi_mean_poly(fr8, polys, nv)
+    monkeypatch.delenv("VHR_POLY_PIXEL")
+    np.testing.assert_array_equal(c_scan.cpu().numpy(), c_pix.cpu().numpy())
+    np.testing.assert_array_equal(m_scan.cpu().numpy(), m_pix.cpu().numpy())          # NaN == NaN for empty sets
+    mask = eng.poly_mask(T, H, W, polys, nv)
+    np.testing.assert_array_equal(mask.sum(dim=(2, 3)).cpu().numpy(), c_scan.cpu().numpy())
+    assert int(c_scan.sum()) > 0
+
+
 # --------------------------------------------------------------------------------------- BPM
 def test_bpm_golden(vhr, eng, golden_dir):
     """Identical BPM (hence identical spectral-peak bin) as the reference's estimators on the

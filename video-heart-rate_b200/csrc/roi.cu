@@ -8,6 +8,7 @@
 // and cheek outlines are drawn INTO the frame before the cheek slice is averaged) using the
 // thickness-2 cv.rectangle raster model pinned in oracle/roi.py:outline_mask.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -159,6 +160,141 @@ __global__ void __launch_bounds__(RT) poly_mean_kernel(const Tpix* __restrict__ 
     }
 }
 
+// ---- scanline form of the same rule ----------------------------------------------------------
+// The per-pixel test above costs O(vertices) int64 cross products per pixel of the bounding box
+// (33 ms per 1080p clip for a forehead + two cheek polygons).  Per row y the rule decomposes:
+//   * parity: an edge that straddles y ((y0 <= y) != (y1 <= y)) counts for the pixels strictly left
+//     of its crossing xc, i.e. for x < ceil(xc) (exact int64 rational).  The number of straddling
+//     edges of a closed polygon is even, so parity(x) = (number of edges with ceil(xc) <= x) mod 2:
+//     toggle one bit per edge at ceil(xc) and take the inclusive prefix-XOR along the row;
+//   * on-edge pixels: a horizontal edge at y contributes a run, any other edge at most the one lattice
+//     point it passes through at y (dx (y - y0) divisible by dy).
+// One warp per row, one lane per edge; the row mask lives in shared memory as bits.
+constexpr int SCAN_MAXW = 256;          // mask words per row: bounding boxes up to 8192 pixels wide
+
+__device__ __forceinline__ void scan_row_mask(int y, const int2* __restrict__ v, int n, int bx0, int bw,
+                                              uint32_t* __restrict__ tog, uint32_t* __restrict__ edg) {
+    const int lane = threadIdx.x & 31;
+    const int nw = (bw + 31) >> 5;
+    for (int w = lane; w < nw; w += 32) { tog[w] = 0u; edg[w] = 0u; }
+    __syncwarp();
+    for (int e = lane; e < n; e += 32) {
+        const int2 a = v[e], b = v[e + 1 == n ? 0 : e + 1];
+        const long long dx = (long long)b.x - a.x, dy = (long long)b.y - a.y;
+        if (dy == 0) {
+            if (a.y == y) {                                         // horizontal edge (or a repeated vertex) on this row
+                const int c0 = max(min(a.x, b.x), bx0) - bx0, c1 = min(max(a.x, b.x), bx0 + bw - 1) - bx0;
+                for (int w = c0 >> 5; c0 <= c1 && w <= (c1 >> 5); ++w) {
+                    const int lo = max(c0 - 32 * w, 0), hi = min(c1 - 32 * w, 31);
+                    atomicOr(&edg[w], (0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo));
+                }
+            }
+            continue;
+        }
+        long long num = dx * ((long long)y - a.y), den = dy;
+        if (den < 0) { num = -num; den = -den; }
+        if (y >= min(a.y, b.y) && y <= max(a.y, b.y) && num % den == 0) {       // lattice point of the segment on this row
+            const long long x = (long long)a.x + num / den;
+            if (x >= bx0 && x < (long long)bx0 + bw) atomicOr(&edg[(int)(x - bx0) >> 5], 1u << ((int)(x - bx0) & 31));
+        }
+        if ((a.y <= y) != (b.y <= y)) {
+            long long q = num / den;                                 // ceil(num / den), den > 0
+            if (num > 0 && num % den != 0) ++q;
+            const long long xi = (long long)a.x + q;                 // pixels x < xi are left of the crossing
+            if (xi < (long long)bx0 + bw) {
+                const int c = xi <= bx0 ? 0 : (int)(xi - bx0);
+                atomicXor(&tog[c >> 5], 1u << (c & 31));
+            }
+        }
+    }
+    __syncwarp();
+    // inclusive prefix-XOR along the row, 32 words per step
+    uint32_t carry = 0u;                                             // parity of all toggles in the words before this step
+    for (int w0 = 0; w0 < nw; w0 += 32) {
+        const int w = w0 + lane;
+        uint32_t m = w < nw ? tog[w] : 0u;
+        uint32_t par = __popc(m) & 1u;                               // parity of this word
+        uint32_t inc = par;                                          // inclusive scan of the word parities over the lanes
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc ^= o;
+        }
+        m ^= m << 1; m ^= m << 2; m ^= m << 4; m ^= m << 8; m ^= m << 16;
+        if ((inc ^ par ^ carry) & 1u) m = ~m;                        // parity of everything left of this word
+        if (w < nw) {
+            m |= edg[w];
+            if (w == nw - 1 && (bw & 31)) m &= 0xFFFFFFFFu >> (32 - (bw & 31));
+            tog[w] = m;
+        }
+        carry ^= __shfl_sync(0xffffffffu, inc, 31);
+    }
+    __syncwarp();
+}
+
+template <typename Tpix>
+__global__ void __launch_bounds__(RT) poly_mean_scan_kernel(const Tpix* __restrict__ frames, int H, int W,
+                                                             const int32_t* __restrict__ poly, const int32_t* __restrict__ nvert,
+                                                             int K, int Vmax, double* __restrict__ mean, long long* __restrict__ count) {
+    __shared__ int2 verts[VHR_MAX_POLY_VERTS];
+    __shared__ uint32_t rowmask[RT / 32][2][SCAN_MAXW];
+    __shared__ double shd[RT / 32];
+    __shared__ unsigned long long shu[RT / 32];
+    const int t = blockIdx.x / K, k = blockIdx.x - t * K;
+    int n = nvert[(size_t)t * K + k];
+    n = min(max(n, 0), min(Vmax, VHR_MAX_POLY_VERTS));
+    const int32_t* pv = poly + (((size_t)t * K + k) * Vmax) * 2;
+    for (int i = threadIdx.x; i < n; i += RT) verts[i] = make_int2(pv[2 * i], pv[2 * i + 1]);
+    __syncthreads();
+    int bx0 = W, by0 = H, bx1 = -1, by1 = -1;
+    for (int i = 0; i < n; ++i) {
+        bx0 = min(bx0, verts[i].x); bx1 = max(bx1, verts[i].x);
+        by0 = min(by0, verts[i].y); by1 = max(by1, verts[i].y);
+    }
+    bx0 = max(bx0, 0); by0 = max(by0, 0); bx1 = min(bx1, W - 1); by1 = min(by1, H - 1);
+    const int bw = bx1 - bx0 + 1, bh = by1 - by0 + 1;
+    const Tpix* fr = frames + (size_t)t * H * W * 3;
+    double s0 = 0, s1 = 0, s2 = 0;
+    unsigned long long u0 = 0, u1 = 0, u2 = 0, cnt = 0;
+    if (n > 0 && bw > 0 && bh > 0) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        uint32_t* tog = rowmask[warp][0];
+        uint32_t* edg = rowmask[warp][1];
+        for (int y = by0 + warp; y <= by1; y += RT / 32) {
+            scan_row_mask(y, verts, n, bx0, bw, tog, edg);
+            const Tpix* row = fr + ((size_t)y * W + bx0) * 3;
+            for (int c0 = 0; c0 < bw; c0 += 32) {
+                const uint32_t m = tog[c0 >> 5];                     // warp-uniform word
+                if (m == 0u) continue;
+                if ((m >> lane) & 1u) {
+                    const Tpix* p = row + (size_t)(c0 + lane) * 3;
+                    if (sizeof(Tpix) == 1) { u0 += (unsigned)p[0]; u1 += (unsigned)p[1]; u2 += (unsigned)p[2]; }
+                    else { s0 += (double)p[0]; s1 += (double)p[1]; s2 += (double)p[2]; }
+                }
+                if (lane == 0) cnt += __popc(m);
+            }
+            __syncwarp();                                            // the mask is rebuilt for the warp's next row
+        }
+    }
+    const unsigned long long ctot = block_sum(cnt, shu);
+    double t0, t1, t2;
+    if (sizeof(Tpix) == 1) {
+        t0 = (double)block_sum(u0, shu); t1 = (double)block_sum(u1, shu); t2 = (double)block_sum(u2, shu);
+    } else {
+        t0 = block_sum(s0, shd); t1 = block_sum(s1, shd); t2 = block_sum(s2, shd);
+    }
+    if (threadIdx.x == 0) {
+        double* out = mean + ((size_t)t * K + k) * 3;
+        if (ctot == 0) {
+            out[0] = out[1] = out[2] = __longlong_as_double(0x7FF8000000000000ll);
+        } else {
+            const double nn = (double)ctot;
+            out[0] = __ddiv_rn(t0, nn); out[1] = __ddiv_rn(t1, nn); out[2] = __ddiv_rn(t2, nn);
+        }
+        if (count) count[(size_t)t * K + k] = (long long)ctot;
+    }
+}
+
 __global__ void __launch_bounds__(RT) poly_mask_kernel(int H, int W, const int32_t* __restrict__ poly,
                                                         const int32_t* __restrict__ nvert, int K, int Vmax,
                                                         uint8_t* __restrict__ mask) {
@@ -202,6 +338,12 @@ static int poly_mean_impl(vhr_ctx* ctx, const Tpix* d_frames, int T, int H, int 
     VHR_REQUIRE(ctx, d_frames && d_poly && d_nvert && d_mean, "null pointer");
     VHR_REQUIRE(ctx, T >= 1 && H >= 1 && W >= 1 && K >= 1, "bad shape");
     VHR_REQUIRE(ctx, Vmax >= 1 && Vmax <= VHR_MAX_POLY_VERTS, "Vmax must be 1..64");
+    const char* px = getenv("VHR_POLY_PIXEL");                 // test hook: the per-pixel form of the rule
+    if (W <= 32 * SCAN_MAXW && !(px && px[0] == '1')) {
+        poly_mean_scan_kernel<Tpix><<<(unsigned)((size_t)T * K), RT, 0, (cudaStream_t)stream>>>(
+            d_frames, H, W, d_poly, d_nvert, K, Vmax, d_mean, reinterpret_cast<long long*>(d_count));
+        return vhr_after_launch(ctx, "poly_mean_scan_kernel");
+    }
     poly_mean_kernel<Tpix><<<(unsigned)((size_t)T * K), RT, 0, (cudaStream_t)stream>>>(
         d_frames, H, W, d_poly, d_nvert, K, Vmax, d_mean, reinterpret_cast<long long*>(d_count));
     return vhr_after_launch(ctx, "poly_mean_kernel");
