@@ -71,22 +71,9 @@ __device__ void detrend_window(double* x, float* xf, int n, int mode) {
     __syncthreads();
 }
 
-// |X_k|^2 of x[0..n) (float64), twiddles from a table tw[m] = (cos, sin)(2 pi m / n)
-__device__ __forceinline__ double dft_power(const double* x, int n, int k, const double2* tw) {
-    double re = 0., im = 0.;
-    int m = 0;
-    for (int i = 0; i < n; ++i) {
-        const double2 w = tw[m];
-        re = fma(x[i], w.x, re);
-        im = fma(-x[i], w.y, im);
-        m += k;
-        if (m >= n) m -= n;
-    }
-    return re * re + im * im;
-}
-
-// same sum with the 32 lanes of a warp striding over the samples (butterfly reduction: every
-// lane ends with the same value)
+// |X_k|^2 of x[0..n) (float64), twiddles from a table tw[m] = (cos, sin)(2 pi m / n):
+// the 32 lanes of a warp stride over the samples (butterfly reduction: every lane ends with the
+// same value)
 __device__ __forceinline__ double dft_power_warp(const double* x, int n, int k, const double2* tw) {
     const int lane = threadIdx.x & 31;
     double re = 0., im = 0.;
@@ -165,7 +152,6 @@ __global__ void __launch_bounds__(BT) bpm_fft_kernel(const FftArgs a) {
     ArgMax best;
     best.v = 0.;
     best.k = -1;
-    int best_col = -1;
     for (int c = 0; c < a.C; ++c) {
         __syncthreads();
         for (int i = threadIdx.x; i < n; i += BT) x[i] = a.trace[(size_t)(s + i) * a.C + c];
@@ -184,9 +170,8 @@ __global__ void __launch_bounds__(BT) bpm_fft_kernel(const FftArgs a) {
         }
         const ArgMax col = block_argmax(mine, shm);
         // best channel: first maximum of the per-channel peak magnitudes
-        if (col.k >= 0 && (best.k < 0 || col.v > best.v)) { best = col; best_col = c; }
+        if (col.k >= 0 && (best.k < 0 || col.v > best.v)) best = col;
     }
-    (void)best_col;
     if (threadIdx.x == 0) {
         if (best.k < 0) { a.bpm[w] = qnan(); a.bin[w] = -1; }
         else { a.bpm[w] = __dmul_rn(np_freq(best.k, n, a.fs), 60.0); a.bin[w] = best.k; }
