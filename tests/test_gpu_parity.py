@@ -187,6 +187,46 @@ def test_collapse_addback(vhr, eng, hw, levels):
         assert np.isnan(m[t, 2]).all()                 # empty rectangle -> NaN like np.mean([])
 
 
+def test_full_size_properties_1080p(vhr, eng):
+    """BASELINE's full frame size (1920x1080, 4 levels, 0.7-4 Hz, alpha 50), checked through properties
+    that need no oracle: (1) a static clip has no energy in the band, so the magnified output is the input,
+    bit for bit; (2) the ideal filter is circular in time, so rolling the clip rolls the output; (3) pyramid
+    level 4 of the whole cascade has the chain's size (68 x 120); (4) the fused ROI sums over the whole
+    frame equal the mean of the output tensor; (5) rectangle and polygon ROI means of the same axis-aligned
+    region agree."""
+    import torch
+    T, H, W = 60, 1080, 1920
+    g = torch.Generator(device="cpu").manual_seed(3)
+    one = torch.randint(0, 256, (1, H, W, 3), dtype=torch.uint8, generator=g).to(eng.tdev)
+    static = one.expand(T, H, W, 3).contiguous()
+    r = eng.evm(static, 30.0, 4, 0.7, 4.0, 50.0, out_f32=True)
+    assert torch.equal(r["out_f32"], static.float())
+    del r, static
+    spec = vhr.SynthSpec(T=T, H=H, W=W, fps=30.0, pulse_hz=1.5, seed=7)
+    clip = eng.synth_clip(spec)
+    full = np.tile(np.array([0, 0, W, H], dtype=np.int32), (T, 1, 1))
+    lvl = eng.pyrdown(clip, 4)
+    assert tuple(lvl.shape) == (T, 68, 120, 3)
+    a = eng.evm(clip, 30.0, 4, 0.7, 4.0, 50.0, rects=full, out_f32=True)
+    out = a["out_f32"]
+    got = a["roi_mean"][:, 0, :].cpu().numpy()
+    exp = out.double().mean(dim=(1, 2)).cpu().numpy()
+    assert np.abs(got - exp).max() <= REL * np.abs(exp).max()
+    k = 17
+    b = eng.evm(torch.roll(clip, k, dims=0), 30.0, 4, 0.7, 4.0, 50.0, out_f32=True)["out_f32"]
+    d = (torch.roll(out, k, dims=0) - b).abs().max().item()
+    assert d <= REL * out.abs().max().item()
+    del b
+    x0, y0, x1, y1 = 700, 400, 1200, 650
+    rect = np.tile(np.array([x0, y0, x1, y1], dtype=np.int32), (T, 1, 1))
+    poly = np.tile(np.array([[x0, y0], [x1 - 1, y0], [x1 - 1, y1 - 1], [x0, y1 - 1]], dtype=np.int32), (T, 1, 1, 1))
+    nv = np.full((T, 1), 4, dtype=np.int32)
+    mr = eng.roi_mean_rect(clip, rect).cpu().numpy()
+    mp_, cnt = eng.roi_mean_poly(clip, poly, nv)
+    np.testing.assert_array_equal(mr, mp_.cpu().numpy())                 # both exact integer sums / count
+    assert int(cnt[0, 0]) == (x1 - x0) * (y1 - y0)
+
+
 def test_evm_end_to_end_c1(vhr, eng):
     """Config c1 (256x144, 5 FPS, 30 s, 1.2 Hz): EVM + ROI + BPM against the oracle."""
     s, o = spec_pair(vhr, T=150, H=144, W=256, fps=5.0, pulse_hz=1.2, seed=0)
