@@ -8,6 +8,7 @@ Tolerances (stated up front, SURVEY.md section 7 "hard parts"):
     traces: max |a - b| <= 1e-4 * max |b| (relative to the tensor's scale).
 """
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -18,6 +19,8 @@ from oracle import roi as oroi
 from oracle import synth as osynth
 
 pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 REL = 1e-4
 
@@ -408,6 +411,60 @@ def test_green_avg_measure_matches_oracle(vhr, eng):
         green = [oroi.rect_mean(f, rect)[1] for f in fr]
         exp, _ = obpm.green_avg_series(green, fps)
         np.testing.assert_array_equal(got, exp)
+
+
+def test_measurement_plugins_through_a_video_file(vhr, eng, tmp_path, monkeypatch):
+    """The reference-facing boundary itself: `analysis/main.py:29-31` does
+    importlib.import_module(f"measurement.{name}").measure(video_path).  A synthetic clip is written
+    losslessly (FFV1) with a landmark side-car; the plugins are imported from a harness-like directory
+    the same way; green_avg_b200 must return the reference loop's (N,2) array (oracle: green_avg.py
+    restated, pinned by the golden vectors) on the DECODED frames, evm_b200 the injected pulse."""
+    import importlib
+    import shutil
+    import cv2
+    fps, T, H, W = 30.0, 330, 144, 256
+    s, o = spec_pair(vhr, T=T, H=H, W=W, fps=fps, pulse_hz=1.4, seed=11)
+    frames = osynth.synth_frames(o)
+    path = str(tmp_path / "subject.mkv")
+    wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"FFV1"), fps, (W, H))
+    if not wr.isOpened():
+        pytest.skip("cv2 build has no FFV1 writer")
+    for f in frames:
+        wr.write(f)
+    wr.release()
+    lm = o.landmarks()
+    np.save(str(tmp_path / "subject.landmarks.npy"), np.tile(lm[None], (T, 1, 1)))
+    harness = tmp_path / "analysis" / "measurement"
+    harness.mkdir(parents=True)
+    src = os.path.join(ROOT, "video-heart-rate_b200", "analysis", "measurement")
+    for name in ("green_avg_b200.py", "evm_b200.py", "green_avg_psd_b200.py"):
+        shutil.copy(os.path.join(src, name), str(harness / name))
+    (harness / "__init__.py").write_text("")
+    monkeypatch.syspath_prepend(str(tmp_path / "analysis"))
+    monkeypatch.chdir(str(tmp_path / "analysis"))
+    for m in [k for k in sys.modules if k == "measurement" or k.startswith("measurement.")]:
+        monkeypatch.delitem(sys.modules, m)
+    ga = importlib.import_module("measurement.green_avg_b200")
+    got = ga.measure(path)
+    cap = cv2.VideoCapture(path)
+    dec = []
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        dec.append(f)
+    cap.release()
+    assert len(dec) == T and np.array_equal(np.stack(dec), frames)          # FFV1 is lossless
+    rect = oroi.cheek_roi_from_bbox(oroi.bbox_from_landmarks_clamped(lm[:, 0], lm[:, 1], W, H), W, H)
+    green = [oroi.rect_mean(f, rect)[1] for f in dec]
+    exp, _ = obpm.green_avg_series(green, fps)
+    assert got.dtype == np.float64 and got.shape == exp.shape and got.shape[1] == 2
+    np.testing.assert_array_equal(got, exp)
+    ev = importlib.import_module("measurement.evm_b200").measure(path)
+    assert ev.shape[1] == 2 and len(ev) == T - int(10 * fps) + 1
+    assert np.all(np.abs(ev[:, 1] - 84.0) <= 6.0)                           # 1.4 Hz pulse, 6 BPM bins at 10 s
+    with pytest.raises(FileNotFoundError):
+        ga.measure(str(tmp_path / "missing.mkv"))                            # video_io.py:10-11 behaviour
 
 
 def test_video_bpm_series_matches_oracle(vhr, eng):
