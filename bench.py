@@ -297,19 +297,33 @@ def run_gpu(args):
     # ---- e2e through the host-buffer call ----------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        h_frames = torch.empty((T, H, W, 3), dtype=torch.uint8, pin_memory=True)
-        h_frames.copy_(clips[0])
+        # one clip per rank in pinned host memory (11.2 GB at 1080p); if the host cannot pin that much for
+        # every rank, the same call runs on the first third of the clip (frames/s is per frame either way)
+        T_e = T
+        try:
+            h_frames = torch.empty((T_e, H, W, 3), dtype=torch.uint8, pin_memory=True)
+        except RuntimeError:
+            torch.cuda.empty_cache()
+            T_e = max(T // 3, 1)
+            h_frames = torch.empty((T_e, H, W, 3), dtype=torch.uint8, pin_memory=True)
+        if world > 1:                 # every rank runs the same number of frames
+            t_min = torch.tensor([T_e], dtype=torch.int64, device=dev)
+            dist.all_reduce(t_min, op=dist.ReduceOp.MIN)
+            T_e = int(t_min.item())
+            h_frames = h_frames[:T_e]
+        h_frames.copy_(clips[0][:T_e])
         torch.cuda.synchronize()
         clips.clear()                 # free the device-timed buffers before the host path allocates its own
         out = lvl = None
         torch.cuda.empty_cache()
         fr_np = h_frames.numpy()
-        rects_np = np.tile(rect, (T, 1, 1)).astype(np.int32)
+        rects_np = np.tile(rect, (T_e, 1, 1)).astype(np.int32)
+        lens_e = torch.full((1,), T_e, dtype=torch.int32, device=dev)
         ke = max(2, min(args.e2e_steps, K))
 
         def e2e_step():
             means = eng.evm_roi_host(fr_np, fps, rects_np, LEVELS, F_LO, F_HI, ALPHA)      # H2D + kernels + D2H
-            bpm, _ = eng.bpm_fft(means[:, 0, 1], starts, lens, fps, ANALYSIS_BAND, detrend=vhr.DETREND_F32, max_len=T)
+            bpm, _ = eng.bpm_fft(means[:, 0, 1], starts, lens_e, fps, ANALYSIS_BAND, detrend=vhr.DETREND_F32, max_len=T_e)
             return float(bpm[0].item())                                                    # D2H of the result
 
         e2e_step()
@@ -323,8 +337,9 @@ def run_gpu(args):
         if world > 1:
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
         dt = float(t_e.item())
-        e2e = {"value": world * ke * T / dt, "unit": "frames/s", "h2d_bytes_per_step": int(T * H * W * 3 + T * 16),
-               "d2h_bytes_per_step": int(T * 24 + 8), "steps": ke, "ms_per_step": 1e3 * dt / ke, "bpm": b,
+        e2e = {"value": world * ke * T_e / dt, "unit": "frames/s", "h2d_bytes_per_step": int(T_e * H * W * 3 + T_e * 16),
+               "d2h_bytes_per_step": int(T_e * 24 + 8), "steps": ke, "ms_per_step": 1e3 * dt / ke, "bpm": b,
+               "frames_per_step_per_gpu": T_e,
                "api": "Engine.evm_roi_host (vhr_evm_roi_host) + Engine.bpm_fft, pinned host frames"}
 
     # ---- CPU baseline (rank 0, N == 1 only) ---------------------------------------------------
