@@ -300,38 +300,50 @@ __device__ __forceinline__ void fft_pass(float2* __restrict__ z, const float2* _
     }
 }
 
-// the same pass for the composite radices (8, 9): one work item = one butterfly of one series
-// (the R - 1 outer twiddles no longer fit in registers beside the R values, and T / R butterflies
-// alone would leave most of the block idle)
+// the same pass for the composite radices (8, 9): the outer twiddles of a butterfly are loaded once
+// and reused for the FG series (the kernel is bound by shared-memory wavefronts, and the R - 1
+// twiddle loads per butterfly and series nearly doubled the read traffic of these passes)
 template <int R, bool INV>
 __device__ __forceinline__ void fft_pass_big(float2* __restrict__ z, const float2* __restrict__ tws, int T, int n,
                                              unsigned inv_m, const float* __restrict__ mask) {
     const int m = n / R, step = T / n, nb = T / R;
-    for (int it = threadIdx.x; it < nb * FG; it += FT) {
-        const int s = it / nb, b = it - s * nb;
+    for (int b = threadIdx.x; b < nb; b += FT) {
         const int block = inv_m ? (int)__umulhi((unsigned)b, inv_m) : b;     // inv_m == 0 encodes m == 1
         const int j = b - block * m;
         const int base = block * n + j;
-        float2* zs = z + (size_t)s * T + base;
         const int js = j * step;
-        float2 v[R];
+        float2 w[R];
+        if (js != 0) {
 #pragma unroll
-        for (int q = 0; q < R; ++q) v[q] = zs[q * m];
-        if (INV && js != 0) {
-#pragma unroll
-            for (int q = 1; q < R; ++q) v[q] = cmul(v[q], tws[js * q]);
+            for (int q = 1; q < R; ++q) { const float2 t = tws[js * q]; w[q] = make_float2(t.x, INV ? t.y : -t.y); }
         }
-        dft_small<R, INV>(v);
-        if (!INV && js != 0) {
-#pragma unroll
-            for (int q = 1; q < R; ++q) { const float2 t = tws[js * q]; v[q] = cmul(v[q], make_float2(t.x, -t.y)); }
-        }
+        float mk[R];
         if (mask) {
 #pragma unroll
-            for (int q = 0; q < R; ++q) { const float mk = __ldg(mask + base + q * m); v[q] = make_float2(v[q].x * mk, v[q].y * mk); }
+            for (int q = 0; q < R; ++q) mk[q] = __ldg(mask + base + q * m);
         }
+#pragma unroll 1
+        for (int s = 0; s < FG; ++s) {
+            float2* zs = z + (size_t)s * T + base;
+            float2 v[R];
 #pragma unroll
-        for (int q = 0; q < R; ++q) zs[q * m] = v[q];
+            for (int q = 0; q < R; ++q) v[q] = zs[q * m];
+            if (INV && js != 0) {
+#pragma unroll
+                for (int q = 1; q < R; ++q) v[q] = cmul(v[q], w[q]);
+            }
+            dft_small<R, INV>(v);
+            if (!INV && js != 0) {
+#pragma unroll
+                for (int q = 1; q < R; ++q) v[q] = cmul(v[q], w[q]);
+            }
+            if (mask) {
+#pragma unroll
+                for (int q = 0; q < R; ++q) v[q] = make_float2(v[q].x * mk[q], v[q].y * mk[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < R; ++q) zs[q * m] = v[q];
+        }
     }
 }
 
