@@ -176,7 +176,7 @@ struct Stream {
     float* out_frame;
     int nextr[3], lastr[3];            // levels 1, 2 (levels >= 3: DutyState)
     int seg_next[VHR_MAX_LEVELS + 1], seg_last[VHR_MAX_LEVELS + 1];
-    uint32_t w0[6], w1[6], w2[6];      // level-1 H rows carried between level-1 rows
+    uint32_t VA[12], VC[12];           // level-1 vertical pass: partial sum of the next row, last input row (split layout)
 
     __device__ Stream(const StreamArgs& a_, const CUtensorMap* tm, unsigned char* s, int col)
         : a(a_), tmap(tm), smem(s), i(col), own((threadIdx.x & 31) >= 1 && (threadIdx.x & 31) <= LANES && col < a_.nt),
@@ -231,47 +231,103 @@ struct Stream {
             while (g_issued < lim) issue_group(g_issued++);
         }
     }
-    // level-1 horizontal pass of one ring row (6 packed registers)
-    __device__ __forceinline__ void hrow(const unsigned char* p, uint32_t (&hp)[6]) {
-        uint32_t wd[9];
-        const uint2 q0 = *reinterpret_cast<const uint2*>(p), q1 = *reinterpret_cast<const uint2*>(p + 8);
-        const uint2 q2 = *reinterpret_cast<const uint2*>(p + 16), q3 = *reinterpret_cast<const uint2*>(p + 24);
-        wd[8] = *reinterpret_cast<const uint32_t*>(p + 32);
-        wd[0] = q0.x; wd[1] = q0.y; wd[2] = q1.x; wd[3] = q1.y; wd[4] = q2.x; wd[5] = q2.y; wd[6] = q3.x; wd[7] = q3.y;
-        if (first_col) {                                       // pixels -2,-1 reflect to 2,1
-            wd[0] = __byte_perm(wd[3], 0, 0x3244);
-            const uint32_t tt = __byte_perm(wd[2], wd[3], 0x5430);
-            wd[1] = __byte_perm(tt, wd[4], 0x3214);
+    // ---- level 1, vertical pass first ---------------------------------------------------------
+    // A lane reads only its own 24 bytes of a row (3 x LDS.64).  Each word is split into two
+    // registers of two 16-bit lanes (bytes 0,2 and bytes 1,3): the vertical 5-tap then runs on packed
+    // values (<= 4080) for two bytes per instruction, and only ONE row per level-1 row goes through
+    // the horizontal pass (3 IDP2A per value on same-channel pixel pairs; the neighbours' pairs come
+    // by shuffle).  Per level-1 row r the vertical pass is incremental:
+    //     out_r = A + 4 n1 + n2,   A' = C + 4 n1 + 6 n2,   C' = n2
+    // with n1, n2 the new rows 2r+1, 2r+2, C = row 2r and A = row(2r-2) + 4 row(2r-1) + 6 row(2r).
+    // All sums are exact integers (level 1 = sum / 256), identical to the horizontal-first order.
+    __device__ __forceinline__ void load_unpack(const unsigned char* p, uint32_t (&u)[12]) {
+        const uint2 q0 = *reinterpret_cast<const uint2*>(p + 8), q1 = *reinterpret_cast<const uint2*>(p + 16);
+        const uint2 q2 = *reinterpret_cast<const uint2*>(p + 24);
+        const uint32_t w[6] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y};
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            u[2 * k] = __byte_perm(w[k], 0u, 0x4240);            // bytes 0, 2
+            u[2 * k + 1] = __byte_perm(w[k], 0u, 0x4341);        // bytes 1, 3
         }
-        if (last_col) wd[8] = __byte_perm(wd[6], wd[7], 0x0432);   // pixel W reflects to W-2
-        HPass<0>::run(wd, hp);
     }
-    // Next group of the segment -> the level-1 horizontal passes of its two rows.
-    template <bool FIRST>
-    __device__ __forceinline__ void consume(uint32_t (&ha)[6], uint32_t (&hb)[6]) {
+    // (register, half) of element e = 3 px + ch of the lane's 24 values in the split layout
+    __host__ __device__ static constexpr int el_reg(int e) { return 2 * (e >> 2) + (e & 1); }
+    __host__ __device__ static constexpr int el_half(int e) { return (e & 3) >> 1; }
+    // same-channel pair (px 2k, px 2k+1) of channel c from the split layout: one PRMT
+    template <int K, int CH>
+    __device__ __forceinline__ uint32_t pair_of(const uint32_t (&v)[12]) const {
+        constexpr int e1 = 6 * K + CH, e2 = e1 + 3;
+        constexpr uint32_t sel = (uint32_t)(2 * el_half(e1)) | ((uint32_t)(2 * el_half(e1) + 1) << 4) |
+                                 ((uint32_t)(4 + 2 * el_half(e2)) << 8) | ((uint32_t)(4 + 2 * el_half(e2) + 1) << 12);
+        return __byte_perm(v[el_reg(e1)], v[el_reg(e2)], sel);
+    }
+    template <int CH>
+    __device__ __forceinline__ void hpass_channel(const uint32_t (&vv)[12], uint32_t (&out)[6]) {
+        const uint32_t p0 = pair_of<0, CH>(vv), p1 = pair_of<1, CH>(vv), p2 = pair_of<2, CH>(vv), p3 = pair_of<3, CH>(vv);
+        uint32_t pl = __shfl_up_sync(0xffffffffu, p3, 1);          // px -2, -1
+        uint32_t pr = __shfl_down_sync(0xffffffffu, p0, 1);        // px 8
+        if (first_col) pl = __byte_perm(p1, p0, 0x7610);           // px -2,-1 <- px 2,1
+        if (last_col) pr = p3;                                     // px 8 <- px 6
+        uint32_t o0 = __dp2a_lo(pl, 0x0401u, 0u);
+        o0 = __dp2a_lo(p0, 0x0406u, o0);
+        o0 = __dp2a_lo(p1, 0x0001u, o0);
+        uint32_t o1 = __dp2a_lo(p0, 0x0401u, 0u);
+        o1 = __dp2a_lo(p1, 0x0406u, o1);
+        o1 = __dp2a_lo(p2, 0x0001u, o1);
+        uint32_t o2 = __dp2a_lo(p1, 0x0401u, 0u);
+        o2 = __dp2a_lo(p2, 0x0406u, o2);
+        o2 = __dp2a_lo(p3, 0x0001u, o2);
+        uint32_t o3 = __dp2a_lo(p2, 0x0401u, 0u);
+        o3 = __dp2a_lo(p3, 0x0406u, o3);
+        o3 = __dp2a_lo(pr, 0x0001u, o3);
+        out[2 * CH] = __byte_perm(o0, o1, 0x5410);                 // level-1 px 4i, 4i+1 (values <= 65280)
+        out[2 * CH + 1] = __byte_perm(o2, o3, 0x5410);             // level-1 px 4i+2, 4i+3
+    }
+    // wait for the next group of the segment; returns the address of its first row for this lane
+    __device__ __forceinline__ const unsigned char* next_group() {
         mbar_wait(wbar + 8 * c_g, (uint32_t)c_phase);
         const unsigned char* p = rd + c_g * GBYTES;
-        if constexpr (!FIRST) hrow(p, ha);              // (the first row of a segment's group 0 is a filler)
-        hrow(p + WSLOT, hb);
         ++g_cons;
         if (++c_g == a.ng) { c_g = 0; c_phase ^= 1; }
+        return p;
     }
 
-    // ---- level 1: one row = two new input rows + the packed vertical pass ---------------------
     __device__ __forceinline__ void prime() {       // first three input rows of a segment
-        uint32_t filler[6];
-        consume<true>(filler, w0);
-        consume<false>(w1, w2);
+        const unsigned char* p = next_group();      // (the first row of a segment's group 0 is a filler)
+        uint32_t x0[12], x1[12];
+        load_unpack(p + WSLOT, x0);
+        p = next_group();
+        load_unpack(p, x1);
+        load_unpack(p + WSLOT, VC);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) VA[k] = x0[k] + (x1[k] << 2) + VC[k] * 6u;
         refill();
     }
     __device__ __forceinline__ void l1_row(uint32_t (&v)[6]) {
-        uint32_t w3[6], w4[6];
-        consume<false>(w3, w4);
+        const unsigned char* p = next_group();
+        uint32_t vv[12];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {      // packed 16-bit lanes (max 65280: no carry between halves)
-            v[k] = (w0[k] + w4[k]) + ((w1[k] + w3[k]) << 2) + w2[k] * 6u;
-            w0[k] = w2[k]; w1[k] = w3[k]; w2[k] = w4[k];
+        for (int h = 0; h < 3; ++h) {      // one LDS.64 of each new row at a time: 8 of the 24 values
+            const uint2 qa = *reinterpret_cast<const uint2*>(p + 8 + 8 * h);
+            const uint2 qb = *reinterpret_cast<const uint2*>(p + WSLOT + 8 + 8 * h);
+            const uint32_t wa[2] = {qa.x, qa.y}, wb[2] = {qb.x, qb.y};
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+#pragma unroll
+                for (int par = 0; par < 2; ++par) {
+                    const int k = 4 * h + 2 * j + par;
+                    const uint32_t n1 = __byte_perm(wa[j], 0u, par ? 0x4341 : 0x4240);
+                    const uint32_t n2 = __byte_perm(wb[j], 0u, par ? 0x4341 : 0x4240);
+                    const uint32_t t = n1 << 2;
+                    vv[k] = VA[k] + t + n2;                 // <= 4080 per 16-bit lane
+                    VA[k] = VC[k] + t + n2 * 6u;
+                    VC[k] = n2;
+                }
+            }
         }
+        hpass_channel<0>(vv, v);
+        hpass_channel<1>(vv, v);
+        hpass_channel<2>(vv, v);
     }
     // level-2 horizontal pass of a finished level-1 row: neighbours' pixels by shuffle
     __device__ __forceinline__ void l2_hrow(const uint32_t (&v)[6], uint32_t (&o)[6]) {
