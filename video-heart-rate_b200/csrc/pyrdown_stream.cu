@@ -88,47 +88,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-// ---- level-1 horizontal pass: compile-time IDP4A weight words ---------------------------------
-__host__ __device__ constexpr int fdiv4(int b) { return b >= 0 ? b / 4 : -((-b + 3) / 4); }
-__host__ __device__ constexpr uint32_t tap_word(int j0, int wi) {
-    uint32_t r = 0;
-    const int wt[5] = {1, 4, 6, 4, 1};
-    for (int d = 0; d < 5; ++d) {
-        int b = j0 + 3 * (d - 2);
-        int w = fdiv4(b);
-        if (w == wi) r |= (uint32_t)wt[d] << (8 * (b - 4 * w));
-    }
-    return r;
-}
-template <int O, int WI>
-struct Tap {
-    __device__ static __forceinline__ uint32_t run(const uint32_t (&wd)[9], uint32_t acc) {
-        constexpr uint32_t k = tap_word(6 * (O / 3) + (O % 3), WI);
-        if (k != 0) acc = __dp4a(wd[WI + 2], k, acc);
-        return Tap<O, WI + 1>::run(wd, acc);
-    }
-};
-template <int O>
-struct Tap<O, 7> {
-    __device__ static __forceinline__ uint32_t run(const uint32_t (&)[9], uint32_t acc) { return acc; }
-};
-// 12 outputs (pixel m = 0..3, channel c) -> 6 packed registers: hp[2c] = (m0 | m1 << 16),
-// hp[2c+1] = (m2 | m3 << 16)
-template <int C>
-struct HPass {
-    __device__ static __forceinline__ void run(const uint32_t (&wd)[9], uint32_t (&hp)[6]) {
-        const uint32_t o0 = Tap<0 + C, -2>::run(wd, 0u), o1 = Tap<3 + C, -2>::run(wd, 0u);
-        const uint32_t o2 = Tap<6 + C, -2>::run(wd, 0u), o3 = Tap<9 + C, -2>::run(wd, 0u);
-        hp[2 * C] = __byte_perm(o0, o1, 0x5410);
-        hp[2 * C + 1] = __byte_perm(o2, o3, 0x5410);
-        HPass<C + 1>::run(wd, hp);
-    }
-};
-template <>
-struct HPass<3> {
-    __device__ static __forceinline__ void run(const uint32_t (&)[9], uint32_t (&)[6]) {}
-};
-
 // vector loads / stores of C consecutive floats (C = 4, 2, 1), naturally aligned
 template <int C>
 __device__ __forceinline__ void ldv(const float* p, float* x) {
