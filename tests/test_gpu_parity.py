@@ -274,6 +274,40 @@ def test_rect_means_golden(vhr, eng, golden_dir):
         np.testing.assert_array_equal(v.cpu().numpy()[0], g[f"px_video_green_{i}"])
 
 
+@pytest.mark.parametrize("shape", [(5, 7), (61, 67), (144, 256), (90, 1919)])
+def test_rect_rows_kernel_equals_per_pixel(vhr, eng, shape, monkeypatch):
+    """The row-wise rectangle mean (aligned words + IDP4A per channel, head/tail masks) against the
+    per-pixel kernel and NumPy: every start phase, widths 1..W, rectangles touching the clip's last byte,
+    empty and out-of-frame rectangles (NaN)."""
+    import torch
+    H, W = shape
+    rng = np.random.default_rng(H + W)
+    T, K = 5, 6
+    fr = rng.integers(0, 256, (T, H, W, 3), dtype=np.uint8)
+    rects = np.zeros((T, K, 4), dtype=np.int32)
+    for t in range(T):
+        for k in range(K):
+            x1, x2 = np.sort(rng.integers(0, W + 1, 2)); y1, y2 = np.sort(rng.integers(0, H + 1, 2))
+            rects[t, k] = (x1, y1, x2, y2)
+    rects[-1, 0] = (0, 0, W, H)                       # whole frame, ends on the clip's last byte
+    rects[-1, 1] = (W - 1, H - 1, W, H)               # the last pixel
+    rects[0, 2] = (3, 2, 3, 4)                        # empty
+    rects[0, 3] = (0, 0, W + 1, H)                    # out of frame
+    frd = torch.as_tensor(fr, device=eng.tdev)
+    rows = eng.roi_mean_rect(frd, rects).cpu().numpy()
+    monkeypatch.setenv("VHR_RECT_PIXEL", "1")
+    pix = eng.roi_mean_rect(frd, rects).cpu().numpy()
+    monkeypatch.delenv("VHR_RECT_PIXEL")
+    np.testing.assert_array_equal(rows, pix)
+    for t in range(T):
+        for k in range(K):
+            x1, y1, x2, y2 = rects[t, k]
+            if x2 > x1 and y2 > y1 and x2 <= W:
+                np.testing.assert_array_equal(rows[t, k], fr[t, y1:y2, x1:x2].reshape(-1, 3).mean(0))
+            else:
+                assert np.isnan(rows[t, k]).all()
+
+
 def test_poly_mask_and_means(vhr, eng):
     import torch
     rng = np.random.default_rng(5)

@@ -85,6 +85,80 @@ __global__ void __launch_bounds__(RT) rect_mean_u8_kernel(const uint8_t* __restr
     }
 }
 
+// The same means without a paint list (the analysis harness' clean ROI, green_avg.py:34): one warp per
+// ROI row, aligned 4-byte loads, three IDP4A per word (one per channel, the byte -> channel phase of a
+// word is (byte offset) mod 3), head and tail bytes masked off.  Exact integer sums, so the means are
+// bit-identical to the per-pixel kernel above.
+__global__ void __launch_bounds__(RT) rect_mean_u8_rows_kernel(const uint8_t* __restrict__ frames, size_t total_bytes,
+                                                                int H, int W, const int32_t* __restrict__ rects, int K,
+                                                                double* __restrict__ mean) {
+    __shared__ unsigned long long sh[RT / 32];
+    const int t = blockIdx.x / K, k = blockIdx.x - t * K;
+    const int32_t* rc = rects + ((size_t)t * K + k) * 4;
+    const int x1 = rc[0], y1 = rc[1], x2 = rc[2], y2 = rc[3];
+    const int rw = x2 - x1, rh = y2 - y1;
+    double* out = mean + ((size_t)t * K + k) * 3;
+    if (rw <= 0 || rh <= 0 || x1 < 0 || y1 < 0 || x2 > W || y2 > H) {
+        if (threadIdx.x < 3) out[threadIdx.x] = __longlong_as_double(0x7FF8000000000000ll);
+        return;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;       // (frames: 4-byte aligned, checked by the caller)
+    unsigned s0 = 0, s1 = 0, s2 = 0;                                  // <= 255 * 4 * words per lane: far below 2^32
+    unsigned long long a0 = 0, a1 = 0, a2 = 0;
+    for (int r = warp; r < rh; r += RT / 32) {
+        const size_t b0 = ((size_t)(y1 + r) * W + x1) * 3 + (size_t)t * H * W * 3;   // byte offset from `frames`
+        const size_t w0 = b0 >> 2;                                     // the row's first aligned word
+        const int head = (int)(b0 - (w0 << 2));                        // bytes of that word before the row (0..3)
+        const int nbytes = rw * 3;
+        const int nwords = (head + nbytes + 3) >> 2;
+        const uint32_t* __restrict__ wp = reinterpret_cast<const uint32_t*>(frames) + w0;
+        const bool clip_tail = ((w0 + nwords) << 2) > total_bytes;     // the clip's last, partial word is in this row
+        constexpr int UB = 8;                                          // words per lane in flight (the loop is pure load latency otherwise)
+        for (int wb = lane; wb < nwords; wb += 32 * UB) {
+            uint32_t v[UB];
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const int idx = wb + 32 * u;
+                v[u] = 0;
+                if (idx < nwords) {
+                    if (!(clip_tail && idx == nwords - 1)) {
+                        v[u] = __ldg(wp + idx);
+                    } else {
+                        const size_t o = (w0 + idx) << 2;
+                        for (int j = 0; o + j < total_bytes; ++j) v[u] |= (uint32_t)frames[o + j] << (8 * j);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const int d = 4 * (wb + 32 * u) - head;                 // offset of the word's byte 0 from the row's first byte (>= -3)
+                uint32_t x = v[u];
+                if (d < 0) x &= 0xFFFFFFFFu << (8 * -d);                // head bytes of the row's first word
+                if (d + 4 > nbytes) x &= (d < nbytes) ? 0xFFFFFFFFu >> (8 * (d + 4 - nbytes)) : 0u;   // tail bytes of its last word
+                const unsigned ph = (unsigned)(d + 3) % 3u;             // channel of byte 0
+                // weight words: byte j counts for channel c iff (ph + j) % 3 == c
+                const uint32_t m0 = ph == 0 ? 0x01000001u : (ph == 1 ? 0x00010000u : 0x00000100u);
+                const uint32_t m1 = ph == 0 ? 0x00000100u : (ph == 1 ? 0x01000001u : 0x00010000u);
+                const uint32_t m2 = ph == 0 ? 0x00010000u : (ph == 1 ? 0x00000100u : 0x01000001u);
+                s0 = __dp4a(x, m0, s0);
+                s1 = __dp4a(x, m1, s1);
+                s2 = __dp4a(x, m2, s2);
+            }
+        }
+        a0 += s0; a1 += s1; a2 += s2;
+        s0 = s1 = s2 = 0;
+    }
+    const unsigned long long t0 = block_sum(a0, sh);
+    const unsigned long long t1 = block_sum(a1, sh);
+    const unsigned long long t2 = block_sum(a2, sh);
+    if (threadIdx.x == 0) {
+        const double n = (double)rw * (double)rh;
+        out[0] = __ddiv_rn((double)t0, n);
+        out[1] = __ddiv_rn((double)t1, n);
+        out[2] = __ddiv_rn((double)t2, n);
+    }
+}
+
 // ---- polygons ----------------------------------------------------------------------------
 // inside(x,y) = on any edge (closed segment) OR even-odd parity with half-open spans
 // (y0 <= y) != (y1 <= y) and the pixel strictly left of the crossing -- oracle/roi.py:poly_mask.
@@ -327,6 +401,12 @@ extern "C" int vhr_roi_mean_rect_u8(vhr_ctx* ctx, const uint8_t* d_frames, int T
     pa.np = NP;
     for (int p = 0; p < NP; ++p)
         for (int c = 0; c < 3; ++c) pa.rgb[p][c] = paint_rgb[p * 3 + c];
+    const char* px = getenv("VHR_RECT_PIXEL");                 // test hook: the per-pixel kernel
+    if (NP == 0 && (reinterpret_cast<uintptr_t>(d_frames) & 3) == 0 && !(px && px[0] == '1')) {
+        rect_mean_u8_rows_kernel<<<(unsigned)((size_t)T * K), RT, 0, (cudaStream_t)stream>>>(d_frames, (size_t)T * H * W * 3, H, W,
+                                                                                              d_rects, K, d_mean);
+        return vhr_after_launch(ctx, "rect_mean_u8_rows_kernel");
+    }
     rect_mean_u8_kernel<<<(unsigned)((size_t)T * K), RT, 0, (cudaStream_t)stream>>>(d_frames, H, W, d_rects, K, d_paint, pa, d_mean);
     return vhr_after_launch(ctx, "rect_mean_u8_kernel");
 }
