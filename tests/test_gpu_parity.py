@@ -595,3 +595,25 @@ def test_config_runners_reduced(vhr, eng):
     assert r1["bpm_butter_last"] == pytest.approx(73.3333, abs=1e-3) and r1["evm_bpm"] == 72.0
     r5 = rc.run_c5(eng, vhr, n=20)
     assert r5["windows"] == 20 and r5["nan_windows"] == 0 and r5["mae_bpm"] <= 3.0
+
+
+def test_bench_gpu_arm_prints_the_contract_line():
+    """`bench.py` (GPU arm) on the small c1 workload: the JSON line carries the contract's keys
+    (roofline, cpu_baseline, e2e with transfer bytes, gpu_launches, clocks) and a correct BPM."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "c1", "--steps", "4", "--warmup", "3",
+                          "--e2e-steps", "2"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert key in line, key
+    assert line["n_gpus"] == 1 and line["steps"] == 4 and line["value"] > 0 and line["bpm_ok"] is True
+    assert line["gpu_launches"] == 5 * 4                                   # pyrdown, bandpass, collapse, ROI finalize, BPM
+    r = line["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    e = line["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] >= 150 * 144 * 256 * 3 and e["d2h_bytes_per_step"] > 0
+    c = line["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0
