@@ -1,12 +1,15 @@
 #!/usr/bin/env python
 """bench.py -- 1080p30 frames/s through EVM + ROI + BPM (BASELINE.json metric), one JSON line.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c4|c2|c3|c1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c4|c2|c3|c1] [--roi rect|poly]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A STEP is one pass of the hot path over one synthetic clip per rank: fused pyrDown cascade ->
-temporal ideal bandpass (x alpha) -> collapse + add-back with fused rectangle-ROI means
-(float32 magnified frames written to HBM) -> ROI finalize -> BPM (float32 detrend + FFT peak).
+temporal ideal bandpass (x alpha) -> collapse + add-back with fused ROI means (float32 magnified
+frames written to HBM) -> ROI finalize -> BPM (float32 detrend + FFT peak).  --roi rect (default):
+the reference's clamped cheek rectangle (analysis/utils/roi.py:43-59); --roi poly: forehead + two
+cheek landmark polygons (36 vertices each), rasterised per frame and fused into the same pass,
+BPM from the ROI trace with the strongest peak (estimate_bpm.py:59-64).
 Workload c4 (default): 1920x1080, 30 FPS, 60 s (T = 1800), 4 pyramid levels, 0.7-4 Hz, alpha 50;
 clip i carries a pulse of 0.8 + i*2.4/63 Hz.  Clips are independent, so ranks take clips
 round-robin (weak scaling, no data-path collective; one final gather of the BPMs).
@@ -18,6 +21,8 @@ round-robin (weak scaling, no data-path collective; one final gather of the BPMs
            the BPM inside the timed region.
 `roofline` dominant kernel (collapse + add-back): algorithmic bytes per launch / its mean
            CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs.
+`bpm_ok`   every timed clip's BPM and peak bin equal the CPU ORACLE's for that clip
+           (tests/golden/configs.npz, made by tests/golden/make_config_golden.py).
 `cpu_baseline` / `--impl reference`: the CPU oracle (cv2.pyrDown/pyrUp + np.fft EVM port and the
            reference's own ROI/BPM functions restated) on the host cores, bounded sample.
 """
@@ -52,13 +57,26 @@ def pulse_hz(clip: int) -> float:
 
 
 def recorded_traffic(kernel: str):
-    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/r1_traffic.json);
-    None when there is no record for this workload."""
+    """(DRAM bytes per launch of `kernel`, file) from the newest committed ncu capture record
+    (profiles/r2_traffic.json, else profiles/r1_traffic.json); (None, None) without a record."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            rec = json.load(open(os.path.join(ROOT, "profiles", name)))[kernel]
+            return int(rec["traffic_bytes"]), "profiles/" + name
+        except Exception:
+            continue
+    return None, None
+
+
+def oracle_goldens(workload: str, roi: str):
+    """{clip: (bpm, bin)} from tests/golden/configs.npz: the CPU oracle's result for the clips this
+    workload generates (a data file -- the oracle package itself is not imported on the GPU arm)."""
+    key = {"c4": "c4", "c1": "bench_c1", "c2": "bench_c2", "c3": "bench_c3"}[workload] + ("poly" if roi == "poly" else "")
     try:
-        rec = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[kernel]
-        return int(rec["traffic_bytes"])
+        g = np.load(os.path.join(ROOT, "tests", "golden", "configs.npz"))
+        return {int(c): (float(b), int(k)) for c, b, k in zip(g[key + "_ids"], g[key + "_bpm"], g[key + "_bin"])}
     except Exception:
-        return None
+        return {}
 
 
 def peaks():
@@ -135,12 +153,12 @@ def cpu_reference_run(W, H, fps, T_sample, steps, warmup, frames=None):
     """The oracle (EVM port on cv2/np.fft + reference ROI/BPM restatement) on the host cores.
     Returns (frames_per_s, seconds_per_step list, cores, bpm)."""
     import cv2
-    from oracle import bpm as obpm, evm as oevm, roi as oroi, synth as osynth
+    from oracle import bpm as obpm, evm as oevm, fast as ofast, roi as oroi, synth as osynth
     cores = os.cpu_count() or 1
     cv2.setNumThreads(cores)
     p = osynth.SynthParams(T=T_sample, H=H, W=W, fps=fps, pulse_hz=1.2, seed=0, clip=0)
     if frames is None:
-        frames = osynth.synth_frames(p)
+        frames = ofast.synth_frames(p)
     lm = p.landmarks()
     rect = oroi.cheek_roi_from_bbox(oroi.bbox_from_landmarks_clamped(lm[:, 0], lm[:, 1], W, H), W, H)
     rects = np.tile(np.array(rect, dtype=np.int32), (T_sample, 1, 1))
@@ -173,8 +191,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * total / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "levels": LEVELS, "band_hz": [F_LO, F_HI], "alpha": ALPHA,
-                       "frames_per_step": T_sample},
+            "config": {"workload": desc + f" [CPU arm: each step is a {T_sample}-frame sub-clip of the {T}-frame clip; "
+                                          "frames/s is per frame]", "levels": LEVELS, "band_hz": [F_LO, F_HI], "alpha": ALPHA,
+                       "frames_per_step": T_sample, "frames_per_clip": T, "roi": "1 cheek rectangle"},
             "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t_start}
@@ -215,6 +234,9 @@ def run_gpu(args):
     lm = specs[0].landmarks()
     rect = host.slice_rects(host.cheek_roi_clamped(host.bbox_clamped(lm[None], W, H), W, H), W, H)[0]
     rects = torch.as_tensor(np.tile(rect, (T, 1, 1)).astype(np.int32), device=dev)
+    poly = args.roi == "poly"
+    polys_np, nverts_np = host.face_polygons(np.broadcast_to(lm, (T,) + lm.shape), W, H, n_vertices=36)
+    polys_d, nverts_d = torch.as_tensor(polys_np, device=dev), torch.as_tensor(nverts_np, device=dev)
     out = torch.empty((T, H, W, 3), dtype=torch.float32, device=dev)
     lvl = torch.empty((T, hl, wl, 3), dtype=torch.float32, device=dev)
     starts = torch.zeros(1, dtype=torch.int32, device=dev)      # BPM window list lives on the device
@@ -233,9 +255,13 @@ def run_gpu(args):
         if timed: e[1].record(stream)
         eng.bandpass(lvl, fps, F_LO, F_HI, ALPHA, out=lvl)
         if timed: e[2].record(stream)
-        _, _, means = eng.collapse(lvl, fr, LEVELS, out_f32=out, out_u8=False, rects=rects)
+        if poly:
+            _, _, means = eng.collapse(lvl, fr, LEVELS, out_f32=out, out_u8=False, polys=polys_d, nverts=nverts_d)
+        else:
+            _, _, means = eng.collapse(lvl, fr, LEVELS, out_f32=out, out_u8=False, rects=rects)
         if timed: e[3].record(stream)
-        bpm, kbin = eng.bpm_fft(means[:, 0, 1].contiguous(), starts, lens, fps, ANALYSIS_BAND,
+        # green column(s) of the (T,K,3) trace, read in place (row / column strides)
+        bpm, kbin = eng.bpm_fft(means[:, :, 1] if poly else means[:, 0, 1], starts, lens, fps, ANALYSIS_BAND,
                                 detrend=vhr.DETREND_F32, mode=vhr.FFT_ANALYSIS, max_len=T)
         if timed:
             e[4].record(stream)
@@ -281,16 +307,21 @@ def run_gpu(args):
     path_ms = kt["pyrdown"] + kt["bandpass"] + kt["collapse"]
     path_achieved = bytes_per_frame * T / (path_ms / 1e3) / 1e9
 
-    # ---- BPM check: every timed clip must land on the bin of its injected pulse ------------
+    # ---- BPM check: every timed clip must give the CPU oracle's BPM and peak bin for that clip ------------
+    gold = oracle_goldens(args.workload, args.roi)
     n_fft = T
     bpm_ok = True
+    n_checked = 0
     bpm_local = {}
     for i, (bpm, kbin) in enumerate(results):
         c = my_clips[(Wm + i) % n_res]
-        got = float(bpm[0].item())
-        k_true = int(round(pulse_hz(c) * n_fft / fps))
-        exp = k_true * (1.0 / (n_fft * (1.0 / fps))) * 60.0
-        bpm_ok &= abs(got - exp) < 1e-9
+        got, got_k = float(bpm[0].item()), int(kbin[0].item())
+        if c in gold:
+            bpm_ok &= (got == gold[c][0] and got_k == gold[c][1])
+            n_checked += 1
+        else:       # no oracle record for this clip (other workloads at N > 1): the injected pulse's bin
+            k_true = int(round(pulse_hz(c) * n_fft / fps))
+            bpm_ok &= abs(got - k_true * (1.0 / (n_fft * (1.0 / fps))) * 60.0) < 1e-9
         bpm_local[(Wm + i) % n_res] = [got]
     gathered = parallel.gather_results({my_clips[j]: v for j, v in bpm_local.items()}, world * n_res, 1, device=dev)
 
@@ -318,12 +349,18 @@ def run_gpu(args):
         torch.cuda.empty_cache()
         fr_np = h_frames.numpy()
         rects_np = np.tile(rect, (T_e, 1, 1)).astype(np.int32)
+        polys_e, nverts_e = np.ascontiguousarray(polys_np[:T_e]), np.ascontiguousarray(nverts_np[:T_e])
         lens_e = torch.full((1,), T_e, dtype=torch.int32, device=dev)
         ke = max(2, min(args.e2e_steps, K))
 
         def e2e_step():
-            means = eng.evm_roi_host(fr_np, fps, rects_np, LEVELS, F_LO, F_HI, ALPHA)      # H2D + kernels + D2H
-            bpm, _ = eng.bpm_fft(means[:, 0, 1], starts, lens_e, fps, ANALYSIS_BAND, detrend=vhr.DETREND_F32, max_len=T_e)
+            if poly:                                                                       # H2D + kernels + D2H
+                means = eng.evm_roi_host(fr_np, fps, None, LEVELS, F_LO, F_HI, ALPHA, polys_np=polys_e, nverts_np=nverts_e)
+                sig = means[:, :, 1]
+            else:
+                means = eng.evm_roi_host(fr_np, fps, rects_np, LEVELS, F_LO, F_HI, ALPHA)
+                sig = means[:, 0, 1]
+            bpm, _ = eng.bpm_fft(sig, starts, lens_e, fps, ANALYSIS_BAND, detrend=vhr.DETREND_F32, max_len=T_e)
             return float(bpm[0].item())                                                    # D2H of the result
 
         e2e_step()
@@ -337,10 +374,12 @@ def run_gpu(args):
         if world > 1:
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
         dt = float(t_e.item())
-        e2e = {"value": world * ke * T_e / dt, "unit": "frames/s", "h2d_bytes_per_step": int(T_e * H * W * 3 + T_e * 16),
+        roi_bytes = int(polys_e.nbytes + nverts_e.nbytes) if poly else int(T_e * 16)
+        e2e = {"value": world * ke * T_e / dt, "unit": "frames/s", "h2d_bytes_per_step": int(T_e * H * W * 3) + roi_bytes,
                "d2h_bytes_per_step": int(T_e * 24 + 8), "steps": ke, "ms_per_step": 1e3 * dt / ke, "bpm": b,
                "frames_per_step_per_gpu": T_e,
-               "api": "Engine.evm_roi_host (vhr_evm_roi_host) + Engine.bpm_fft, pinned host frames"}
+               "api": ("Engine.evm_roi_host (vhr_evm_poly_host)" if poly else "Engine.evm_roi_host (vhr_evm_roi_host)")
+                      + " + Engine.bpm_fft, pinned host frames; ROI-only collapse (no magnified frame is materialised)"}
 
     # ---- CPU baseline (rank 0, N == 1 only) ---------------------------------------------------
     cpu = None
@@ -348,6 +387,7 @@ def run_gpu(args):
         T_s = 240 if W >= 1280 else min(T, 150)
         sp = vhr.SynthSpec(T=T_s, H=H, W=W, fps=fps, pulse_hz=1.2, seed=0, clip=0)
         fr_s = eng.synth_clip(sp).cpu().numpy()       # bit-identical to the oracle's generator (tests)
+        eng.trim()                                    # give the host-path arena back before the CPU leg
         v, times, cores, bpm_cpu = cpu_reference_run(W, H, fps, T_s, steps=1, warmup=0, frames=fr_s)
         cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
                "sample": f"{T_s}-frame {W}x{H} sub-clip, one pass of the oracle EVM port (cv2 float32 pyrDown/pyrUp with "
@@ -359,19 +399,22 @@ def run_gpu(args):
                 "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": desc, "levels": LEVELS, "band_hz": [F_LO, F_HI], "alpha": ALPHA,
-                           "frames_per_step_per_gpu": T, "resident_clips_per_gpu": n_res, "roi": "1 cheek rectangle",
+                           "frames_per_step_per_gpu": T, "resident_clips_per_gpu": n_res,
+                           "roi": "forehead + 2 cheeks, 36-vertex polygons (fused row masks)" if poly else "1 cheek rectangle",
                            "bpm": "whole-clip window, float32 detrend + FFT peak",
                            "l2": "inputs (11.2 GB/clip at 1080p) larger than L2; no flush", "parallelism": f"clip-sharded x{world}"},
                 "roofline": {"bound": "hbm", "kernel": "collapse_sep_kernel", "achieved": achieved, "peak": peak_gbs,
                              "unit": "GB/s", "frac": achieved / peak_gbs,
-                             "traffic": recorded_traffic("collapse_sep_kernel") if args.workload == "c4" else None,
-                             "traffic_source": "ncu --set full capture of the same command, profiles/r1_traffic.json",
+                             "traffic": recorded_traffic("collapse_sep_kernel")[0] if args.workload == "c4" else None,
+                             "traffic_source": f"ncu --set full capture of the same command, {recorded_traffic('collapse_sep_kernel')[1]}",
                              "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": collapse_bytes_per_frame * T, "ms_per_launch": col_ms},
                 "path_roofline": {"stages": "pyrdown+bandpass+collapse", "bytes_per_frame": bytes_per_frame,
                                   "achieved": path_achieved, "frac": path_achieved / peak_gbs, "unit": "GB/s"},
                 "kernel_ms": kt, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches) * world,
                 "clocks": clocks, "bpm_ok": bool(bpm_ok),
+                "bpm_check": f"{n_checked} of {len(results)} timed clips on rank 0 against the CPU oracle's BPM and bin "
+                             "(tests/golden/configs.npz); the rest against the injected pulse's bin",
                 "bpm_gathered": None if gathered is None else [round(float(x), 4) for x in gathered[:, 0]]}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -391,6 +434,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--roi", default="rect", choices=["rect", "poly"], help="ROI stage: cheek rectangle, or forehead + cheek polygons")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

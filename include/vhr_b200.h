@@ -15,8 +15,11 @@
  *     *_host entry points, which synchronise before returning.
  *   - Return value: 0 = VHR_OK, negative = error; vhr_last_error(ctx) gives the text.
  *     Nothing throws across the boundary.
- *   - One context per (device, host thread).  A context owns a small scratch arena
- *     (twiddle tables, ROI partial sums) that grows on demand outside the hot loop.
+ *   - One context per (device, host thread), driven by ONE stream at a time.  A context owns
+ *     cached tables (twiddles, band mask, composite pyrUp weights) and a scratch arena (ROI
+ *     partial sums, polygon row masks) that grow on demand outside the hot loop; a call on
+ *     another stream than the context's previous call first waits for that call (event), so
+ *     changing streams between calls is safe, two streams at once are not supported.
  *   - Frames are uint8, interleaved 3-channel, shape (T,H,W,3).  The library is
  *     channel-order agnostic (RGB per BASELINE.json; the reference's cv2 arrays are BGR:
  *     index 1 is green either way).
@@ -34,7 +37,7 @@
 extern "C" {
 #endif
 
-#define VHR_ABI_VERSION 1
+#define VHR_ABI_VERSION 2
 #define VHR_MAX_LEVELS 6
 #define VHR_MAX_ROIS 8
 #define VHR_MAX_POLY_VERTS 64
@@ -91,7 +94,7 @@ int vhr_band_bins(int T, double fps, double f_lo, double f_hi, int* k_first, int
 /* ---- EVM: amplify-collapse-add-back with fused rectangle ROI means ----------------------
  * out(t,y,x,c) = float(frame) + pyrUp^levels(d_level)(t,y,x,c)      (spec = cv2.pyrUp)
  * d_out_f32 (T,H,W,3) float32 and/or d_out_u8 (T,H,W,3) uint8 (clip + round-half-up);
- * either may be NULL.  If K > 0: d_rects int32 (T,K,4), d_roi_mean float64 (T,K,3) gets
+ * either may be NULL.  If K > 0 (<= VHR_MAX_ROIS): d_rects int32 (T,K,4), d_roi_mean float64 (T,K,3) gets
  * the per-channel mean of `out` over each rectangle (replaces get_avg over the cheek
  * slice, rppg_VIDEO.py:60-66,106-110, applied to the magnified frame).  Deterministic:
  * per-tile partial sums, then a fixed-order float64 reduction. */
@@ -100,6 +103,20 @@ int vhr_collapse_addback_roi(vhr_ctx* ctx, const float* d_level, const uint8_t* 
                              float* d_out_f32, uint8_t* d_out_u8,
                              const int32_t* d_rects, int K, double* d_roi_mean,
                              void* stream);
+/* The same pass with landmark-POLYGON ROIs (forehead / cheek outlines; BASELINE.json north_star's
+ * ROI stage; the reference itself only has the rectangles above, rppg_VIDEO.py:102-103):
+ * d_poly int32 (T,K,Vmax,2) vertices (x,y), d_nvert int32 (T,K), 1 <= K <= VHR_MAX_ROIS.  Each
+ * polygon is rasterised once per frame by the frozen exact-integer rule of vhr_poly_mask (bit-exact
+ * masks) into row bit-masks, and the collapse accumulates the masked sums of the magnified frame in
+ * the same pass; d_roi_mean (T,K,3) = masked mean (NaN for an empty mask), d_count int64 (T,K)
+ * (optional) = pixels in each mask.
+ * In both calls, when d_out_f32 == d_out_u8 == NULL only the image parts under a ROI are
+ * evaluated (ROI-only mode: the measurement plugins' case). */
+int vhr_collapse_addback_poly(vhr_ctx* ctx, const float* d_level, const uint8_t* d_frames,
+                              int T, int H, int W, int levels,
+                              float* d_out_f32, uint8_t* d_out_u8,
+                              const int32_t* d_poly, const int32_t* d_nvert, int K, int Vmax,
+                              double* d_roi_mean, int64_t* d_count, void* stream);
 
 /* ---- ROI on raw uint8 frames -------------------------------------------------------------
  * Rectangle means, bit-exact with np.mean(roi[:,:,c]) in float64 (exact integer sums):
@@ -126,7 +143,10 @@ int vhr_poly_mask(vhr_ctx* ctx, int T, int H, int W, const int32_t* d_poly,
                   const int32_t* d_nvert, int K, int Vmax, uint8_t* d_mask, void* stream);
 
 /* ---- BPM estimation ----------------------------------------------------------------------
- * Batched over windows of one or more traces.  d_trace float64 (n_trace, C) time-major.
+ * Batched over windows of one or more traces.  d_trace float64 (n_trace, C) time-major: sample i of
+ * column c at d_trace[i * ld + c * cs] (contiguous: ld = C, cs = 1; the green means of the K ROIs
+ * of a (T,K,3) trace: pointer to element [0,0,1], C = K, ld = 3K, cs = 3).  With C > 1 the chosen
+ * bin is the per-column peak of the column with the largest peak (estimate_bpm.py:59-64).
  * Window w covers samples [start[w], start[w]+len[w]); max_len >= every len[w] (it sizes the
  * shared memory; windows longer than max_len yield NaN).  Results: d_bpm float64 (n_win)
  * (NaN where the reference returns None), d_bin int32 (n_win) = chosen FFT/rfft bin.
@@ -139,7 +159,7 @@ enum { VHR_DETREND_NONE = 0, VHR_DETREND_F64 = 1, VHR_DETREND_F32 = 2, VHR_DETRE
 /* analysis/utils/estimate_bpm.py:12-65 (mode 0: |X| over freqs>0, N>=8 required) and
  * rppg_VIDEO.py:129-147 (mode 1: mask on signed fftfreq, no length floor). */
 enum { VHR_FFT_ANALYSIS = 0, VHR_FFT_VIDEO = 1 };
-int vhr_bpm_fft(vhr_ctx* ctx, const double* d_trace, int n_trace, int C,
+int vhr_bpm_fft(vhr_ctx* ctx, const double* d_trace, int n_trace, int C, int ld, int cs,
                 const int32_t* d_start, const int32_t* d_len, int n_win, int max_len,
                 double fs, double f_lo, double f_hi, int detrend, int mode,
                 double* d_bpm, int32_t* d_bin, void* stream);
@@ -171,11 +191,12 @@ int vhr_sos_causal(vhr_ctx* ctx, const double* d_x, int n, const double* h_sos, 
 
 /* ---- analysis-harness degradations and metric ---------------------------
  * Additive noise: clip(float(frame) + noise, 0, 255) truncated to uint8 -- analysis/degradation/
- * colour_noise.py:11-24.  The noise is a counter-based hash (std = noise_gain_q8 * 147.8 / 256
- * LSB) of (seed, clip, t0 + t, byte index) so the CPU oracle regenerates it bit for bit; the
- * reference draws np.random.normal.  In place allowed. */
+ * colour_noise.py:11-24.  The reference draws np.random.normal; here the draw is a counter-based
+ * 12-term Irwin-Hall sum (twelve hash bytes of (seed, clip, t0 + t, byte index); mean 0,
+ * std = noise_gain_q16 * 255.998 / 65536 LSB, tails to 5.98 std) in pure integer arithmetic, so
+ * the CPU oracle regenerates it bit for bit.  In place allowed. */
 int vhr_degrade_noise_u8(vhr_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int T, int H, int W,
-                         int noise_gain_q8, uint32_t seed, uint32_t clip, int t0, void* stream);
+                         int noise_gain_q16, uint32_t seed, uint32_t clip, int t0, void* stream);
 /* Bit-depth quantisation: scale = 256 // 2**bits; (x // scale) * scale -- analysis/degradation/
  * colour_quantisation.py:12-25 (bits > 8 gives all zeros, like NumPy's uint8 // 0). */
 int vhr_degrade_quantise_u8(vhr_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, long long n, int bits,
@@ -188,11 +209,20 @@ int vhr_align_mae(vhr_ctx* ctx, const double* d_truth_t, const double* d_truth_h
 
 /* ---- host-buffer convenience (the reference-facing call: NumPy arrays in and out) -------
  * Whole EVM + ROI path on one clip held in HOST memory: H2D of the frames, the three EVM
- * kernels, fused ROI means, D2H of the (T,K,3) float64 ROI trace.  h_out_f32 may be NULL
- * (the magnified frames then stay on the device in a context-owned buffer). */
+ * kernels, fused ROI means, D2H of the (T,K,3) float64 ROI trace.  h_out_f32 may be NULL: the
+ * magnified frames are then never materialised (ROI-only collapse).  h_frames should be
+ * page-locked (pageable memory works but its copies do not overlap the kernels).  The device
+ * arena of these calls stays cached in the context until vhr_trim / vhr_destroy. */
 int vhr_evm_roi_host(vhr_ctx* ctx, const uint8_t* h_frames, int T, int H, int W, int levels,
                      double fps, double f_lo, double f_hi, float alpha,
                      const int32_t* h_rects, int K, double* h_roi_mean, float* h_out_f32);
+/* Polygon form: h_poly int32 (T,K,Vmax,2), h_nvert int32 (T,K); h_count int64 (T,K) optional. */
+int vhr_evm_poly_host(vhr_ctx* ctx, const uint8_t* h_frames, int T, int H, int W, int levels,
+                      double fps, double f_lo, double f_hi, float alpha,
+                      const int32_t* h_poly, const int32_t* h_nvert, int K, int Vmax,
+                      double* h_roi_mean, int64_t* h_count, float* h_out_f32);
+/* Release the context's cached device buffers (host-path arena, scratch arena). */
+int vhr_trim(vhr_ctx* ctx);
 
 #ifdef __cplusplus
 }

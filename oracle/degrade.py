@@ -2,16 +2,19 @@
 
 ``quantise_colour``  analysis/degradation/colour_quantisation.py:12-25 (verbatim arithmetic)
 ``add_noise``        analysis/degradation/colour_noise.py:11-24 with the reference's
-                     ``np.random.normal`` replaced by the repository's counter-based hash noise
-                     (same clip + ``astype(uint8)`` truncation), so the CUDA kernel can be held to it
-                     bit for bit; the distribution (mean 0, std sigma) is what the reference draws.
+                     ``np.random.normal`` replaced by a counter-based 12-term Irwin-Hall draw (sum of
+                     twelve hash bytes: mean 0, std sigma, tails to +-5.98 sigma, excess kurtosis
+                     -0.1; same clip + ``astype(uint8)`` truncation), pure integer arithmetic so the
+                     CUDA kernel can be held to it bit for bit.
 ``align_truth`` / ``mae``  analysis/utils/video_io.py:80-106, analysis/metrics/mae.py:32-36
 """
 from __future__ import annotations
 
 import numpy as np
 
-from .synth import BYTE_SUM_STD, mix32
+from .synth import mix32
+
+NOISE_SUM_STD = float(np.sqrt(12.0 * (256.0**2 - 1.0) / 12.0))   # twelve uniform bytes: 255.998
 
 
 def quantise_colour(frame: np.ndarray, bits: int) -> np.ndarray:
@@ -22,7 +25,8 @@ def quantise_colour(frame: np.ndarray, bits: int) -> np.ndarray:
 
 
 def noise_gain(sigma: float) -> int:
-    return int(round(sigma * 256.0 / BYTE_SUM_STD))
+    """Q16 gain per unit of the centred twelve-byte sum."""
+    return int(round(sigma * 65536.0 / NOISE_SUM_STD))
 
 
 def add_noise(frames: np.ndarray, sigma: float, seed: int = 0, clip: int = 0, t0: int = 0) -> np.ndarray:
@@ -36,10 +40,13 @@ def add_noise(frames: np.ndarray, sigma: float, seed: int = 0, clip: int = 0, t0
     out = np.empty_like(frames)
     flat = frames.reshape(T, -1).astype(np.int32)
     for i in range(T):
-        r = mix32(keys[i] ^ idx)
-        s = ((r & np.uint32(255)) + ((r >> np.uint32(8)) & np.uint32(255)) + ((r >> np.uint32(16)) & np.uint32(255))
-             + (r >> np.uint32(24))).astype(np.int32) - 510
-        v = (flat[i] * 256 + s * gain) >> 8
+        s = np.full(idx.shape, -1530, dtype=np.int32)
+        for w in range(3):
+            with np.errstate(over="ignore"):
+                r = mix32((keys[i] + np.uint32(w) * np.uint32(0x9E3779B9)) ^ idx)
+            s += ((r & np.uint32(255)) + ((r >> np.uint32(8)) & np.uint32(255)) + ((r >> np.uint32(16)) & np.uint32(255))
+                  + (r >> np.uint32(24))).astype(np.int32)
+        v = (flat[i] * 65536 + s * gain) >> 16
         out[i] = np.clip(v, 0, 255).astype(np.uint8).reshape(H, W, C)
     return out
 

@@ -176,3 +176,73 @@ def evm_clip_cv2(frames: np.ndarray, fps: float, levels: int = 4, f_lo: float = 
                 if roi.size:
                     means[t, k] = roi.reshape(-1, 3).mean(axis=0, dtype=np.float64)
     return lv, filt, out, means
+
+
+def evm_roi_trace_streaming(frame_chunks, T: int, H: int, W: int, fps: float, rects: np.ndarray | None = None,
+                            levels: int = 4, f_lo: float = 0.7, f_hi: float = 4.0, alpha: float = 50.0,
+                            polys: np.ndarray | None = None, nverts: np.ndarray | None = None):
+    """``evm_clip_cv2(...)[3]`` (the (T,K,3) ROI means of the magnified frames) for clips too large
+    to hold: ``frame_chunks()`` yields consecutive uint8 (n,H,W,3) chunks of the clip.  Same calls in
+    the same order per frame (cv2.pyrDown / cv2.pyrUp float32, np.fft float64); the only difference
+    is that the add-back ``frame.astype(float32) + up`` is evaluated on the union crop of the
+    frame's ROIs instead of the whole frame -- element-wise, so the values are the same
+    (tests/test_oracle.py::test_streaming_trace_equals_clip_form).
+    ROIs: ``rects`` (T,K,4) half-open rectangles, or polygons ``polys`` (T,K,V,2) + ``nverts`` (T,K)
+    rasterised by ``oracle.roi.poly_mask`` (masks are cached per distinct polygon) and averaged with
+    ``oracle.roi.masked_mean``.  -> (level, filtered, means (T,K,3)[, counts (T,K)])."""
+    import cv2
+    from . import roi as oroi
+    dims = pyr_dims(W, H, levels)
+    wl, hl = dims[-1]
+    use_poly = polys is not None
+    K = polys.shape[1] if use_poly else rects.shape[1]
+    lv = np.empty((T, hl, wl, 3), dtype=np.float32)
+    crops, boxes, masks = [], [], []
+    cache = {}
+    t = 0
+    for chunk in frame_chunks():
+        for f in chunk:
+            x = f.astype(np.float32)
+            for _ in range(levels):
+                x = cv2.pyrDown(x)
+            lv[t] = x
+            if use_poly:
+                mk = []
+                for k in range(K):
+                    pts = np.ascontiguousarray(polys[t, k, :nverts[t, k]], dtype=np.int64)
+                    key = pts.tobytes()
+                    if key not in cache:
+                        m = oroi.poly_mask(H, W, pts)
+                        ys, xs = np.nonzero(m)
+                        cache[key] = (m, (int(xs.min()), int(ys.min()), int(xs.max()) + 1, int(ys.max()) + 1) if len(xs) else (0, 0, 0, 0))
+                    mk.append(cache[key])
+                nz = [b for (_, b) in mk if b[2] > b[0]]
+                box = (min(b[0] for b in nz), min(b[1] for b in nz), max(b[2] for b in nz), max(b[3] for b in nz)) if nz else (0, 0, 0, 0)
+                masks.append([m for (m, _) in mk])
+            else:
+                r = rects[t]
+                box = (int(r[:, 0].min()), int(r[:, 1].min()), int(r[:, 2].max()), int(r[:, 3].max()))
+            boxes.append(box)
+            crops.append(f[box[1]:box[3], box[0]:box[2]].copy())
+            t += 1
+    assert t == T
+    filt = (alpha * ideal_bandpass(lv, fps, f_lo, f_hi)).astype(np.float32)
+    means = np.full((T, K, 3), np.nan)
+    counts = np.zeros((T, K), dtype=np.int64)
+    for t in range(T):
+        x = filt[t]
+        for l in range(levels, 0, -1):
+            x = cv2.pyrUp(x, dstsize=dims[l - 1])
+        bx1, by1, bx2, by2 = boxes[t]
+        o = crops[t].astype(np.float32) + x[by1:by2, bx1:bx2]
+        for k in range(K):
+            if use_poly:
+                m = masks[t][k][by1:by2, bx1:bx2]
+                counts[t, k] = int(m.sum())
+                means[t, k] = oroi.masked_mean(o, m)
+            else:
+                x1, y1, x2, y2 = (int(v) for v in rects[t, k])
+                roi = o[y1 - by1:y2 - by1, x1 - bx1:x2 - bx1]
+                if roi.size:
+                    means[t, k] = roi.reshape(-1, 3).mean(axis=0, dtype=np.float64)
+    return (lv, filt, means, counts) if use_poly else (lv, filt, means)

@@ -191,12 +191,71 @@ def gen_metrics(out):
     print("metrics: quantise x6, alignment x4")
 
 
+def gen_bpm_extra(out):
+    """Pins that round 1 left open (bpm_extra.npz):
+    * green_avg_psd_plot.py:34-63 ``_bandpass_butterworth`` / ``_estimate_bpm`` executed on the float32
+      z-scored window of :173-176;
+    * the (T,C) best-column branch of analysis/utils/estimate_bpm.py:59-64 (C = 3);
+    * rppg_VIDEO.py:129-147 ``estimate_bpm`` with FREQ_LOW <= 0 (signed fftfreq mask: DC and the
+      negative-frequency bins become candidates)."""
+    import types
+    P = ref_loader.load_functions("analysis/measurement/green_avg_psd_plot.py", ["_bandpass_butterworth", "_estimate_bpm"])
+    A = ref_loader.load_functions("analysis/utils/estimate_bpm.py", ["estimate_bpm"], extra_ns={"plt": types.SimpleNamespace()})
+    rng = np.random.default_rng(2468)
+    rec = {}
+    i = 0
+    for fps in (5.0, 15.0, 29.97, 30.0):
+        for f_hz in (0.9, 1.45, 2.3):
+            for n_s in (10.0, 12.5):
+                n = int(round(n_s * fps))
+                x = trace(rng, n, fps, f_hz, amp=rng.uniform(0.3, 1.5), noise=rng.uniform(0.05, 0.6), drift=rng.uniform(-0.1, 0.1))
+                sig = np.asarray(x, dtype=np.float32)
+                sig = (sig - np.mean(sig)) / np.std(sig)                               # :174-175
+                filt = P["_bandpass_butterworth"](sig, fps, 40 / 60, 200 / 60, 2)     # :176 (FILTER_ORDER = 2)
+                r = P["_estimate_bpm"](filt, fps)
+                rec[f"psd_x_{i}"] = x
+                rec[f"psd_fps_{i}"] = np.float64(fps)
+                rec[f"psd_bpm_{i}"] = np.float64(r[0] if isinstance(r, tuple) else np.nan)
+                rec[f"psd_filt_{i}"] = np.asarray(filt, dtype=np.float64)
+                i += 1
+    rec["n_psd"] = i
+    j = 0
+    for fps in (5.0, 25.0, 30.0):
+        for n in (int(10 * fps), int(17.3 * fps)):
+            for rep in range(3):
+                amp = rng.uniform(0.2, 2.0, 3)
+                X = np.stack([trace(rng, n, fps, f, amp=a, noise=0.4, base=0.0) for f, a in zip(rng.uniform(0.8, 3.0, 3), amp)], 1)
+                X = X - X.mean(0)
+                bpm = A["estimate_bpm"](X, fps)
+                rec[f"mc_x_{j}"] = X
+                rec[f"mc_fps_{j}"] = np.float64(fps)
+                rec[f"mc_bpm_{j}"] = np.float64(np.nan if bpm is None else bpm)
+                j += 1
+    rec["n_mc"] = j
+    k = 0
+    for (lo, hi) in ((-0.5, 2.0), (0.0, 1.0), (-3.0, -0.7), (0.0, 0.0)):
+        V = ref_loader.load_functions("rppg_VIDEO.py", ["estimate_bpm"])
+        V["__ns__"]["FREQ_LOW"], V["__ns__"]["FREQ_HIGH"] = lo, hi
+        for fps, n in ((30.0, 300), (5.0, 51)):
+            x = trace(rng, n, fps, 1.2, base=rng.choice([0.0, 3.0]))                 # with and without a DC term
+            bpm = V["estimate_bpm"](x, fps)
+            rec[f"vf_x_{k}"] = x
+            rec[f"vf_fps_{k}"] = np.float64(fps)
+            rec[f"vf_band_{k}"] = np.array([lo, hi])
+            rec[f"vf_bpm_{k}"] = np.float64(np.nan if bpm is None else bpm)
+            k += 1
+    rec["n_vf"] = k
+    np.savez_compressed(os.path.join(out, "bpm_extra.npz"), **rec)
+    print("bpm_extra:", i, "psd windows,", j, "multi-column signals,", k, "signed-band cases")
+
+
 def main():
     if not ref_loader.available():
         raise SystemExit("reference tree not found; golden vectors can only be made in the build container")
     gen_roi(HERE)
     gen_bpm(HERE)
     gen_metrics(HERE)
+    gen_bpm_extra(HERE)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,414 @@
+"""GPU parity tests added in round 2 (``-m gpu``): the holes the round-1 review named.
+
+  * the collapse instantiations the headline number times (1920x1080, 4 levels, TMA pixel ring,
+    K = 1 and K = 0) against ``oracle.evm.collapse_addback``;
+  * the BASELINE.json configurations against the CPU ORACLE's traces / BPMs / peak bins
+    (``tests/golden/configs.npz`` <- ``make_config_golden.py``), not against the injected pulse;
+  * polygon ROIs fused into the collapse against ``oracle.roi.poly_mask`` / ``masked_mean``;
+  * ROI-only mode == the full-frame call, bit for bit;
+  * the pins of ``bpm_extra.npz`` (psd-plot variant, (T,3) best column, signed-frequency band);
+  * guard bands around every output buffer on awkward shapes; stream hand-over; noise tails.
+
+Tolerances as in test_gpu_parity.py: integer / index / byte work bit-exact; float32 pixels and ROI
+traces max|a-b| <= 1e-4 * max|b|.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import bpm as obpm
+from oracle import evm as oevm
+from oracle import roi as oroi
+from oracle import synth as osynth
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REL = 1e-4
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def eng(vhr):
+    e = vhr.Engine(0)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def cfg(golden_dir):
+    return np.load(os.path.join(golden_dir, "configs.npz"))
+
+
+def cheek_rects(spec):
+    from video_heart_rate_b200 import host
+    lm = spec.landmarks()
+    r = host.slice_rects(host.cheek_roi_clamped(host.bbox_clamped(lm[None], spec.W, spec.H), spec.W, spec.H), spec.W, spec.H)[0]
+    return np.tile(r, (spec.T, 1, 1)).astype(np.int32)
+
+
+# ------------------------------------------------------------------ collapse at the benchmarked shape
+@pytest.mark.parametrize("K", [1, 0, 3])
+def test_collapse_1080p_against_oracle(vhr, eng, K):
+    """1920x1080, 4 levels, random level-4 input: the composite Ux / Uy tables for 1080 -> 68 rows and
+    1920 -> 120 columns (odd 135 -> 68 step included), the TMA pixel ring (LOAD = 2) and the K = 1 / K = 0 /
+    K = 4 instantiations, against the float64 oracle."""
+    import torch
+    T, H, W, L = 3, 1080, 1920, 4
+    rng = np.random.default_rng(1080 + K)
+    fr = rng.integers(0, 256, (T, H, W, 3), dtype=np.uint8)
+    lv = (40 * rng.standard_normal((T, 68, 120, 3))).astype(np.float32)
+    rects = None
+    if K:
+        rects = np.array([[[624, 421, 1296, 609], [0, 0, W, H], [1900, 1070, 1920, 1080]][:K]] * T, dtype=np.int32)
+    o32, _, means = eng.collapse(torch.as_tensor(lv, device=eng.tdev), torch.as_tensor(fr, device=eng.tdev), L,
+                                 out_f32=True, out_u8=False, rects=rects)
+    ref = oevm.collapse_addback(lv, fr, L)
+    assert rel_err(o32.cpu().numpy(), ref) <= REL
+    if K:
+        m = means.cpu().numpy()
+        for t in range(T):
+            for k in range(K):
+                x1, y1, x2, y2 = rects[t, k]
+                exp = ref[t, y1:y2, x1:x2].reshape(-1, 3).mean(0)
+                assert np.abs(m[t, k] - exp).max() <= REL * np.abs(exp).max()
+
+
+def test_roi_only_mode_is_bit_identical_and_bounds_are_checked(vhr, eng):
+    """No frame output requested -> only items under a ROI run; the ROI means must be the bits of the
+    full-frame call.  Rectangles reaching outside the frame give NaN (like vhr_roi_mean_rect_u8)."""
+    import torch
+    T, H, W, L = 4, 360, 640, 4
+    rng = np.random.default_rng(5)
+    fr = torch.as_tensor(rng.integers(0, 256, (T, H, W, 3), dtype=np.uint8), device=eng.tdev)
+    wl, hl = oevm.pyr_dims(W, H, L)[-1]
+    lv = torch.as_tensor((30 * rng.standard_normal((T, hl, wl, 3))).astype(np.float32), device=eng.tdev)
+    rects = np.array([[[200, 150, 420, 230], [0, 0, 1, 1], [600, 300, 640, 360], [10, 10, 650, 20],
+                       [5, 300, 300, 361], [17, 44, 17, 90]]] * T, dtype=np.int32)          # K = 6: two passes
+    _, _, full = eng.collapse(lv, fr, L, out_f32=True, rects=rects)
+    _, _, only = eng.collapse(lv, fr, L, out_f32=False, out_u8=False, rects=rects)
+    np.testing.assert_array_equal(full.cpu().numpy(), only.cpu().numpy())
+    m = only.cpu().numpy()
+    assert not np.isnan(m[:, :3]).any() and np.isnan(m[:, 3:]).all()
+
+
+# ------------------------------------------------------------------ BASELINE configs vs the CPU oracle
+def _evm_green_and_bpm(eng, vhr, spec, noise=0.0):
+    from video_heart_rate_b200.pipeline import evm_bpm
+    fr = eng.synth_clip(spec)
+    if noise > 0:
+        fr = eng.degrade_noise(fr, noise, seed=spec.seed, clip=spec.clip, out=fr)
+    r = evm_bpm(eng, fr, spec.fps, cheek_rects(spec), 4, (0.7, 4.0), 50.0, out_f32=False)
+    return r["roi_mean"][:, 0, 1].cpu().numpy(), float(r["bpm"][0].item()), int(r["bin"][0].item())
+
+
+@pytest.mark.parametrize("clip", [0, 21, 42, 63])
+def test_c4_clips_match_oracle(vhr, eng, cfg, clip):
+    """Config 4 clips at full size (1920x1080, T = 1800): ROI trace within 1e-4 of the oracle's, identical
+    peak bin, identical BPM."""
+    spec = vhr.SynthSpec(T=1800, H=1080, W=1920, fps=30.0, pulse_hz=0.8 + clip * (2.4 / 63.0), seed=clip, clip=clip)
+    g, bpm, k = _evm_green_and_bpm(eng, vhr, spec)
+    i = int(np.nonzero(cfg["c4_ids"] == clip)[0][0])
+    assert rel_err(g, cfg["c4_trace"][i]) <= REL
+    assert k == int(cfg["c4_bin"][i]) and bpm == float(cfg["c4_bpm"][i])
+
+
+def test_c2_clip_matches_oracle(vhr, eng, cfg):
+    spec = vhr.SynthSpec(T=1800, H=720, W=1280, fps=30.0, pulse_hz=1.2, seed=2)
+    g, bpm, k = _evm_green_and_bpm(eng, vhr, spec)
+    assert rel_err(g, cfg["c2_trace"][0]) <= REL
+    assert k == int(cfg["c2_bin"][0]) and bpm == float(cfg["c2_bpm"][0])
+
+
+def test_c3_windows_match_oracle(vhr, eng, cfg):
+    """Config 3: 640x480 stream, 51 windows of 300 frames every 30 frames, each its own EVM pass."""
+    from video_heart_rate_b200.pipeline import evm_bpm
+    spec = vhr.SynthSpec(T=1800, H=480, W=640, fps=30.0, pulse_hz=1.4, seed=3)
+    fr = eng.synth_clip(spec)
+    rects = cheek_rects(spec)
+    for w in range(51):
+        s = 30 * w
+        r = evm_bpm(eng, fr[s:s + 300], 30.0, rects[s:s + 300], 4, (0.7, 4.0), 50.0, out_f32=False)
+        assert rel_err(r["roi_mean"][:, 0, 1].cpu().numpy(), cfg["c3_trace"][w]) <= REL
+        assert int(r["bin"][0]) == int(cfg["c3_bin"][w]) and float(r["bpm"][0]) == float(cfg["c3_bpm"][w])
+
+
+def test_c5_sweep_matches_oracle(vhr, eng, cfg):
+    """Config 5: all 512 windows (resolution x frame rate x additive noise x pulse): identical peak bin and
+    BPM as the oracle on the identically degraded clips."""
+    from tools import run_configs as rc
+    wins = rc.c5_windows(512)
+    bad = []
+    for (h, fps, sg, f, i) in wins:
+        spec = vhr.SynthSpec(T=int(fps * 10.0), H=h, W=rc.RES[h], fps=float(fps), pulse_hz=f, seed=i, clip=i)
+        _, bpm, k = _evm_green_and_bpm(eng, vhr, spec, noise=sg)
+        eb, ek = float(cfg["c5_bpm"][i]), int(cfg["c5_bin"][i])
+        if not (k == ek and (bpm == eb or (np.isnan(bpm) and np.isnan(eb)))):
+            bad.append((i, h, fps, sg, bpm, eb))
+    assert not bad, f"{len(bad)} of 512 windows differ: {bad[:5]}"
+
+
+# ------------------------------------------------------------------ polygons on the path
+def _face_polys(T, W, H, seed=0, V=36):
+    sys.path.insert(0, ROOT)
+    from tools.bench_roi import polygons
+    return polygons(T, W, H, V=V, seed=seed)
+
+
+@pytest.mark.parametrize("shape", [(1080, 1920), (270, 480), (97, 131)])
+def test_fused_polygon_means_against_oracle(vhr, eng, shape):
+    """Forehead + two cheeks (36-vertex outlines on a jittered track) fused into the collapse: masks are
+    the frozen rule's (pixel counts == oracle.roi.poly_mask, bit-exact), masked means of the magnified
+    frame within 1e-4 of oracle.roi.masked_mean on the oracle's output; the stand-alone polygon kernel on
+    the written output agrees; ROI-only mode gives the same bits."""
+    import torch
+    H, W = shape
+    T, L = 3, 4
+    rng = np.random.default_rng(H + W)
+    fr = rng.integers(0, 256, (T, H, W, 3), dtype=np.uint8)
+    wl, hl = oevm.pyr_dims(W, H, L)[-1]
+    lv = (40 * rng.standard_normal((T, hl, wl, 3))).astype(np.float32)
+    polys, nv = _face_polys(T, W, H, seed=3)
+    polys[2, 1, :, 0] += W // 2                                   # one polygon partly outside the frame
+    frd, lvd = torch.as_tensor(fr, device=eng.tdev), torch.as_tensor(lv, device=eng.tdev)
+    o32, _, means, counts = eng.collapse(lvd, frd, L, out_f32=True, polys=polys, nverts=nv, want_counts=True)
+    ref = oevm.collapse_addback(lv, fr, L)
+    assert rel_err(o32.cpu().numpy(), ref) <= REL
+    m, c = means.cpu().numpy(), counts.cpu().numpy()
+    for t in range(T):
+        for k in range(polys.shape[1]):
+            mask = oroi.poly_mask(H, W, polys[t, k, :nv[t, k]])
+            assert int(c[t, k]) == int(mask.sum())
+            e = oroi.masked_mean(ref[t], mask)
+            assert np.abs(m[t, k] - e).max() <= REL * np.abs(e).max()
+    m2, c2 = eng.roi_mean_poly(o32, polys, nv)
+    np.testing.assert_array_equal(c2.cpu().numpy(), c)
+    assert rel_err(m2.cpu().numpy(), m) <= 1e-6
+    _, _, only = eng.collapse(lvd, frd, L, out_f32=False, out_u8=False, polys=polys, nverts=nv)
+    np.testing.assert_array_equal(only.cpu().numpy(), m)
+
+
+def test_fused_polygon_masks_random_polygons(vhr, eng):
+    """Random simple / self-intersecting / degenerate polygons, K = 5 (two passes), odd width: the fused
+    path's pixel counts equal the mask kernel's, means equal the stand-alone polygon kernel on the output."""
+    import torch
+    H, W, T, K, V, L = 120, 333, 4, 5, 14, 3
+    rng = np.random.default_rng(77)
+    polys = np.zeros((T, K, V, 2), dtype=np.int32)
+    nv = np.zeros((T, K), dtype=np.int32)
+    for t in range(T):
+        for k in range(K):
+            n = int(rng.integers(3, V + 1)) if k < 4 else int(rng.integers(0, 3))
+            polys[t, k, :n] = np.stack([rng.integers(-20, W + 20, n), rng.integers(-10, H + 10, n)], 1)
+            nv[t, k] = n
+    fr = torch.as_tensor(rng.integers(0, 256, (T, H, W, 3), dtype=np.uint8), device=eng.tdev)
+    wl, hl = oevm.pyr_dims(W, H, L)[-1]
+    lv = torch.as_tensor((25 * rng.standard_normal((T, hl, wl, 3))).astype(np.float32), device=eng.tdev)
+    o32, _, means, counts = eng.collapse(lv, fr, L, out_f32=True, polys=polys, nverts=nv, want_counts=True)
+    mask = eng.poly_mask(T, H, W, polys, nv)
+    np.testing.assert_array_equal(mask.sum(dim=(2, 3)).cpu().numpy(), counts.cpu().numpy())
+    m2, _ = eng.roi_mean_poly(o32, polys, nv)
+    a, b = means.cpu().numpy(), m2.cpu().numpy()
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    ok = ~np.isnan(a)
+    assert np.abs(a[ok] - b[ok]).max() <= 1e-6 * np.abs(b[ok]).max()
+
+
+def test_rect_polygon_is_the_rectangle(vhr, eng):
+    """host.ratio_polygons(shape='rect') reproduces the reference's ratio rectangles as 4-gons: the polygon
+    path then returns the rectangle path's ROI means (same pixel set, same accumulation order)."""
+    import torch
+    from video_heart_rate_b200 import host
+    spec = vhr.SynthSpec(T=30, H=144, W=256, fps=5.0, pulse_hz=1.2, seed=1)
+    fr = eng.synth_clip(spec)
+    bb = host.bbox_clamped(np.broadcast_to(spec.landmarks(), (30, 4, 2)), 256, 144)
+    polys, nv = host.ratio_polygons(bb, shape="rect", parts=(("forehead", host.FOREHEAD, (0.0, 1.0)), ("cheek", host.CHEEK, (0.0, 1.0))))
+    rects = np.stack([host.slice_rects(host.roi_coords(bb, *host.FOREHEAD), 256, 144),
+                      host.slice_rects(host.roi_coords(bb, *host.CHEEK), 256, 144)], 1)
+    a = eng.evm(fr, 5.0, 3, 0.7, 4.0, 50.0, rects=rects, out_f32=False)["roi_mean"].cpu().numpy()
+    r = eng.evm(fr, 5.0, 3, 0.7, 4.0, 50.0, polys=polys, nverts=nv, out_f32=False)
+    np.testing.assert_array_equal(r["roi_mean"].cpu().numpy(), a)
+    np.testing.assert_array_equal(r["roi_count"].cpu().numpy(), ((rects[..., 2] - rects[..., 0]) * (rects[..., 3] - rects[..., 1])))
+
+
+def test_evm_poly_host_matches_device_path(vhr, eng):
+    from video_heart_rate_b200 import host
+    s = vhr.SynthSpec(T=60, H=72, W=128, fps=10.0, pulse_hz=1.5, seed=9)
+    fr = osynth.synth_frames(osynth.SynthParams(T=60, H=72, W=128, fps=10.0, pulse_hz=1.5, seed=9))
+    polys, nv = host.face_polygons(np.broadcast_to(s.landmarks(), (60, 4, 2)), 128, 72, n_vertices=20)
+    means, counts = eng.evm_roi_host(fr, 10.0, None, levels=3, polys_np=polys, nverts_np=nv, want_counts=True)
+    import torch
+    r = eng.evm(torch.as_tensor(fr, device=eng.tdev), 10.0, 3, 0.7, 4.0, 50.0, polys=polys, nverts=nv, out_f32=False)
+    np.testing.assert_array_equal(means, r["roi_mean"].cpu().numpy())
+    np.testing.assert_array_equal(counts, r["roi_count"].cpu().numpy())
+    assert counts.min() > 0
+    out = np.empty(fr.shape, dtype=np.float32)
+    m2 = eng.evm_roi_host(fr, 10.0, None, levels=3, polys_np=polys, nverts_np=nv, out=out)
+    np.testing.assert_array_equal(m2, means)
+    full = eng.evm(torch.as_tensor(fr, device=eng.tdev), 10.0, 3, 0.7, 4.0, 50.0, out_f32=True)["out_f32"].cpu().numpy()
+    np.testing.assert_array_equal(out, full)
+    eng.trim()
+
+
+# ------------------------------------------------------------------ BPM pins
+def test_bpm_extra_goldens(vhr, eng, golden_dir):
+    """psd-plot variant, (T,3) best-column branch and the signed-frequency band of the VIDEO estimator
+    against the reference EXECUTED (tests/golden/bpm_extra.npz)."""
+    from video_heart_rate_b200.pipeline import ANALYSIS_BAND, green_avg_psd_series
+    g = np.load(os.path.join(golden_dir, "bpm_extra.npz"))
+    for i in range(int(g["n_psd"])):
+        x, fps = g[f"psd_x_{i}"], float(g[f"psd_fps_{i}"])
+        got = green_avg_psd_series(eng, x, fps, window_s=len(x) / fps, acq_s=len(x) / fps)
+        exp = float(g[f"psd_bpm_{i}"])
+        assert got[-1, 1] == exp or (np.isnan(got[-1, 1]) and np.isnan(exp)), (i, got[-1, 1], exp)
+    for j in range(int(g["n_mc"])):
+        X, fps = g[f"mc_x_{j}"], float(g[f"mc_fps_{j}"])
+        bpm, _ = eng.bpm_fft(X, [0], [len(X)], fps, ANALYSIS_BAND, detrend=vhr.DETREND_NONE, mode=vhr.FFT_ANALYSIS)
+        assert float(bpm[0]) == float(g[f"mc_bpm_{j}"]), j
+    for k in range(int(g["n_vf"])):
+        x, fps = g[f"vf_x_{k}"], float(g[f"vf_fps_{k}"])
+        lo, hi = (float(v) for v in g[f"vf_band_{k}"])
+        bpm, _ = eng.bpm_fft(x, [0], [len(x)], fps, (lo, hi), detrend=vhr.DETREND_NONE, mode=vhr.FFT_VIDEO)
+        exp = float(g[f"vf_bpm_{k}"])
+        assert float(bpm[0]) == exp or (np.isnan(float(bpm[0])) and np.isnan(exp)), (k, float(bpm[0]), exp)
+
+
+def test_bpm_fft_strided_views(vhr, eng):
+    """vhr_bpm_fft reads a column (or K columns) of a (T,K,3) ROI trace in place through ld / cs."""
+    import torch
+    from video_heart_rate_b200.pipeline import ANALYSIS_BAND
+    rng = np.random.default_rng(4)
+    t = np.arange(300) / 30.0
+    tr = rng.standard_normal((300, 3, 3)) * 0.2
+    for k, f in enumerate((1.1, 1.7, 2.4)):
+        tr[:, k, 1] += (0.5 + k) * np.sin(2 * np.pi * f * t)
+    d = torch.as_tensor(tr, device=eng.tdev)
+    for k in range(3):
+        a, ka = eng.bpm_fft(d[:, k, 1], [0], [300], 30.0, ANALYSIS_BAND, detrend=vhr.DETREND_F32)
+        b, kb = eng.bpm_fft(d[:, k, 1].contiguous(), [0], [300], 30.0, ANALYSIS_BAND, detrend=vhr.DETREND_F32)
+        assert float(a[0]) == float(b[0]) and int(ka[0]) == int(kb[0])
+    a, _ = eng.bpm_fft(d[:, :, 1], [0, 10], [300, 290], 30.0, ANALYSIS_BAND, detrend=vhr.DETREND_NONE)
+    for w, (s, n) in enumerate(((0, 300), (10, 290))):
+        exp, _, col = obpm.estimate_bpm_analysis(tr[s:s + n, :, 1], 30.0)
+        assert float(a[w]) == exp and col == 2
+
+
+# ------------------------------------------------------------------ safety
+GUARD = 4096
+
+
+def _guarded(torch, shape, dtype, dev, fill):
+    """A tensor of `shape` carved out of a larger allocation with GUARD bytes of a known pattern either side."""
+    n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+    raw = torch.full((n + 2 * GUARD,), fill, dtype=torch.uint8, device=dev)
+    view = raw[GUARD:GUARD + n].view(dtype).view(shape)
+    return raw, view, n
+
+
+def _guards_intact(raw, n, fill):
+    return bool((raw[:GUARD] == fill).all().item()) and bool((raw[GUARD + n:] == fill).all().item())
+
+
+@pytest.mark.parametrize("case", [(5, 61, 67, 3), (3, 97, 131, 4), (2, 40, 3840, 4), (9, 135, 248, 4), (260, 36, 64, 2),
+                                  (2, 1080, 1920, 4), (4, 33, 700, 3)])
+def test_guard_bands_survive_every_kernel(vhr, eng, case):
+    """Every output buffer of the EVM + ROI + BPM path sits between 4 KiB guard bands of a known pattern;
+    odd sizes, W = 3840 (512-thread pyrDown), shares crossing frames, TMA and scalar paths.  Hand-rolled
+    bulk copies with computed byte counts must not write one byte outside their tensor."""
+    import torch
+    T, H, W, L = case
+    rng = np.random.default_rng(T * H + W)
+    fr = torch.as_tensor(rng.integers(0, 256, (T, H, W, 3), dtype=np.uint8), device=eng.tdev)
+    wl, hl = oevm.pyr_dims(W, H, L)[-1]
+    FILL = 0xA5
+    raw_l, lvl, n_l = _guarded(torch, (T, hl, wl, 3), torch.float32, eng.tdev, FILL)
+    raw_o, o32, n_o = _guarded(torch, (T, H, W, 3), torch.float32, eng.tdev, FILL)
+    raw_u, o8, n_u = _guarded(torch, (T, H, W, 3), torch.uint8, eng.tdev, FILL)
+    eng.pyrdown(fr, L, out=lvl)
+    eng.bandpass(lvl, 10.0, 0.7, 4.0, 50.0, out=lvl)
+    rects = np.tile(np.array([[W // 4, H // 4, W - W // 4, H - H // 4], [0, 0, W, H]], dtype=np.int32), (T, 1, 1))
+    _, _, means = eng.collapse(lvl, fr, L, out_f32=o32, out_u8=o8, rects=rects)
+    polys, nv = _face_polys(T, W, H, seed=1, V=12)
+    _, _, pm = eng.collapse(lvl, fr, L, out_f32=False, out_u8=False, polys=polys, nverts=nv)
+    torch.cuda.synchronize()
+    assert _guards_intact(raw_l, n_l, FILL), "pyrdown / bandpass wrote outside the level tensor"
+    assert _guards_intact(raw_o, n_o, FILL), "collapse wrote outside the float32 output"
+    assert _guards_intact(raw_u, n_u, FILL), "collapse wrote outside the uint8 output"
+    assert torch.isfinite(o32).all() and torch.isfinite(means).all()
+
+
+def test_stream_hand_over(vhr, eng):
+    """A context may be driven from another stream than its previous call (the call waits for the previous
+    one's event): different bands back to back on two streams give the same results as on one stream."""
+    import torch
+    rng = np.random.default_rng(9)
+    x = torch.as_tensor(rng.standard_normal((300, 4096)).astype(np.float32), device=eng.tdev)
+    ref_a = eng.bandpass(x, 30.0, 0.7, 4.0, 50.0).clone()
+    ref_b = eng.bandpass(x, 30.0, 1.0, 2.0, 7.0).clone()
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(5):
+        with torch.cuda.stream(s1):
+            a = eng.bandpass(x, 30.0, 0.7, 4.0, 50.0)
+        with torch.cuda.stream(s2):
+            b = eng.bandpass(x, 30.0, 1.0, 2.0, 7.0)
+        torch.cuda.synchronize()
+        assert torch.equal(a, ref_a) and torch.equal(b, ref_b)
+
+
+def test_noise_tails_on_device(vhr, eng):
+    """The degradation noise reaches beyond the 3.45 sigma bound of the round-1 generator and is the
+    oracle's draw bit for bit on a 720p frame."""
+    import torch
+    from oracle import fast
+    fr = np.full((2, 720, 1280, 3), 128, dtype=np.uint8)
+    got = eng.degrade_noise(torch.as_tensor(fr, device=eng.tdev), 20.0, seed=5, clip=3).cpu().numpy()
+    np.testing.assert_array_equal(got, fast.add_noise(fr, 20.0, seed=5, clip=3))
+    d = got.astype(np.float64) - 128.0
+    assert np.abs(d).max() > 4.2 * 20 and abs(d.std() - 20.0) < 0.5
+
+
+def test_sliding_evm_equals_from_scratch_and_oracle(vhr, eng, cfg):
+    """pipeline.SlidingEvm (config c3 the live way: per hop only the 30 new frames are uploaded from host
+    memory and reduced; the window slides on the device) gives the from-scratch window's ROI trace bit for
+    bit and the CPU oracle's BPM / bin for all 51 windows."""
+    import torch
+    from video_heart_rate_b200.pipeline import SlidingEvm, evm_bpm
+    spec = vhr.SynthSpec(T=1800, H=480, W=640, fps=30.0, pulse_hz=1.4, seed=3)
+    fr = eng.synth_clip(spec)
+    host_frames = fr.cpu()
+    rects = cheek_rects(spec)
+    sl = SlidingEvm(eng, 480, 640, 30.0, 300, 30)
+    assert sl.push(host_frames[:100], rects[:100]) is None and sl.push(host_frames[100:270], rects[100:270]) is None
+    for w in range(51):
+        s = 270 + 30 * w
+        bpm, k = sl.push(host_frames[s:s + 30], rects[s:s + 30])
+        assert k == int(cfg["c3_bin"][w]) and bpm == float(cfg["c3_bpm"][w])
+        if w in (0, 17, 50):
+            r = evm_bpm(eng, fr[30 * w:30 * w + 300], 30.0, rects[30 * w:30 * w + 300], 4, (0.7, 4.0), 50.0, out_f32=False)
+            assert torch.equal(r["roi_mean"], sl.last_means)
+
+
+def test_c4_polygon_clip_matches_oracle(vhr, eng, cfg):
+    """Config 4 with the polygon ROI stage (forehead + two cheeks) at full size: (T,3) green traces within 1e-4
+    of the oracle's (poly_mask + masked_mean on the cv2 EVM output), identical best-column peak bin and BPM."""
+    if "c4poly_ids" not in cfg:
+        pytest.skip("no polygon goldens in configs.npz")
+    from video_heart_rate_b200 import host
+    from video_heart_rate_b200.pipeline import evm_bpm
+    for clip in (0, 42):
+        spec = vhr.SynthSpec(T=1800, H=1080, W=1920, fps=30.0, pulse_hz=0.8 + clip * (2.4 / 63.0), seed=clip, clip=clip)
+        fr = eng.synth_clip(spec)
+        polys, nv = host.face_polygons(np.broadcast_to(spec.landmarks(), (1800, 4, 2)), 1920, 1080)
+        r = evm_bpm(eng, fr, 30.0, None, 4, (0.7, 4.0), 50.0, out_f32=False, polys=polys, nverts=nv)
+        i = int(np.nonzero(cfg["c4poly_ids"] == clip)[0][0])
+        assert rel_err(r["roi_mean"][:, :, 1].cpu().numpy(), cfg["c4poly_trace"][i]) <= REL
+        assert int(r["bin"][0]) == int(cfg["c4poly_bin"][i]) and float(r["bpm"][0]) == float(cfg["c4poly_bpm"][i])
+        del fr, r

@@ -137,7 +137,7 @@ def test_library_exports_every_declared_symbol(pkg):
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     from video_heart_rate_b200 import _lib
     assert set(_lib.SIGNATURES) == declared
-    assert lib.vhr_abi_version() == 1
+    assert lib.vhr_abi_version() == 2
     w = (ctypes.c_int32 * 5)()
     h = (ctypes.c_int32 * 5)()
     assert lib.vhr_pyr_dims(1920, 1080, 4, w, h) == 0

@@ -33,6 +33,8 @@ SIGNATURES = {
     "vhr_band_bins": (c_int, [c_int, c_double, c_double, c_double, C.POINTER(c_int), C.POINTER(c_int)]),
     "vhr_collapse_addback_roi": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                          c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "vhr_collapse_addback_poly": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                          c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "vhr_roi_mean_rect_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int,
                                      c_void_p, c_void_p, c_void_p]),
     "vhr_roi_mean_poly_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
@@ -40,7 +42,7 @@ SIGNATURES = {
     "vhr_roi_mean_poly_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
                                       c_void_p, c_void_p, c_void_p]),
     "vhr_poly_mask": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
-    "vhr_bpm_fft": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_double, c_double,
+    "vhr_bpm_fft": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_double, c_double,
                             c_double, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "vhr_bpm_welch": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_double, c_double, c_double,
                               c_int, c_int, c_void_p, c_int, c_double, c_void_p, c_void_p, c_void_p, c_int,
@@ -52,6 +54,9 @@ SIGNATURES = {
     "vhr_align_mae": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "vhr_evm_roi_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_double, c_double,
                                  c_float, c_void_p, c_int, c_void_p, c_void_p]),
+    "vhr_evm_poly_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_double, c_double,
+                                  c_float, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "vhr_trim": (c_int, [c_void_p]),
 }
 
 _lib = None
@@ -73,7 +78,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.vhr_abi_version() != 1:
+        if lib.vhr_abi_version() != 2:
             raise VhrError("libvhr_b200.so ABI version mismatch")
         _lib = lib
     return _lib

@@ -21,7 +21,14 @@ import numpy as np
 
 
 def read_video(video_path: str):
-    """analysis/utils/video_io.py:8-33: all BGR frames + fps."""
+    """All BGR frames + fps.  Inside the reference's harness (cwd = analysis/) this IS the harness's
+    own reader, ``utils.video_io.read_video`` (analysis/utils/video_io.py:8-33); the few lines below
+    are only the stand-alone fallback with the same behaviour (decode is outside the B200 path)."""
+    try:
+        from utils.video_io import read_video as harness_read_video      # the harness's reader, when installed there
+        return harness_read_video(video_path)
+    except ImportError:
+        pass
     import cv2
     if not os.path.exists(video_path):
         raise FileNotFoundError(f"Video not found: {video_path}")

@@ -34,6 +34,30 @@ int vhr_scratch(vhr_ctx* ctx, size_t bytes, void** out) {
     return VHR_OK;
 }
 
+int vhr_enter(vhr_ctx* ctx, cudaStream_t stream) {
+    if (ctx->have_last && ctx->last_stream != stream)
+        VHR_CHECK_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->last_ev, 0));
+    return VHR_OK;
+}
+
+int vhr_leave(vhr_ctx* ctx, cudaStream_t stream, int rc) {
+    if (!ctx->last_ev) {
+        cudaError_t e = cudaEventCreateWithFlags(&ctx->last_ev, cudaEventDisableTiming);
+        if (e != cudaSuccess) {
+            vhr_set_error(ctx, "cudaEventCreate -> %s", cudaGetErrorString(e));
+            return rc != VHR_OK ? rc : VHR_ERR_CUDA;
+        }
+    }
+    cudaError_t e = cudaEventRecord(ctx->last_ev, stream);
+    if (e != cudaSuccess) {
+        vhr_set_error(ctx, "cudaEventRecord -> %s", cudaGetErrorString(e));
+        return rc != VHR_OK ? rc : VHR_ERR_CUDA;
+    }
+    ctx->last_stream = stream;
+    ctx->have_last = true;
+    return rc;
+}
+
 extern "C" {
 
 int vhr_abi_version(void) { return VHR_ABI_VERSION; }
@@ -54,9 +78,14 @@ int vhr_create(vhr_ctx** out, int device) {
     vhr_ctx* ctx = new (std::nothrow) vhr_ctx();
     if (!ctx) return VHR_ERR_NOMEM;
     ctx->device = device;
-    VHR_CHECK_CUDA(ctx, cudaSetDevice(device));
     cudaDeviceProp prop;
-    VHR_CHECK_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
+    e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        vhr_set_error(nullptr, "vhr_create: device %d -> %s", device, cudaGetErrorString(e));
+        delete ctx;
+        return VHR_ERR_CUDA;
+    }
     if (prop.major < 10) {
         vhr_set_error(nullptr, "vhr_create: device %d is sm_%d%d; this library is built for sm_100a only",
                       device, prop.major, prop.minor);
@@ -77,6 +106,9 @@ int vhr_destroy(vhr_ctx* ctx) {
     if (ctx->mask) cudaFree(ctx->mask);
     if (ctx->hostpath) cudaFree(ctx->hostpath);
     if (ctx->sep_tab) cudaFree(ctx->sep_tab);
+    if (ctx->last_ev) cudaEventDestroy(ctx->last_ev);
+    if (ctx->hp_copy) cudaStreamDestroy(ctx->hp_copy);
+    if (ctx->hp_comp) cudaStreamDestroy(ctx->hp_comp);
     delete ctx;
     return VHR_OK;
 }

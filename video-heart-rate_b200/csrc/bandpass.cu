@@ -444,12 +444,22 @@ static int ensure_twiddles(vhr_ctx* ctx, int T, cudaStream_t stream) {
     return VHR_OK;
 }
 
+static int temporal_bandpass_impl(vhr_ctx* ctx, const float* d_in, float* d_out, int T, int64_t P, double fps,
+                                  double f_lo, double f_hi, float gain, cudaStream_t stream);
+
 extern "C" int vhr_temporal_bandpass(vhr_ctx* ctx, const float* d_in, float* d_out, int T, int64_t P, double fps,
                                      double f_lo, double f_hi, float gain, void* stream_) {
     VHR_REQUIRE(ctx, ctx != nullptr, "null context");
     VHR_REQUIRE(ctx, d_in && d_out, "null pointer");
     VHR_REQUIRE(ctx, T >= 1 && P >= 1 && fps > 0, "bad shape");
     cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = vhr_enter(ctx, stream);           // the twiddle table and the band mask are context-owned
+    if (rc != VHR_OK) return rc;
+    return vhr_leave(ctx, stream, temporal_bandpass_impl(ctx, d_in, d_out, T, P, fps, f_lo, f_hi, gain, stream));
+}
+
+static int temporal_bandpass_impl(vhr_ctx* ctx, const float* d_in, float* d_out, int T, int64_t P, double fps,
+                                  double f_lo, double f_hi, float gain, cudaStream_t stream) {
     int k0 = -1, k1 = -1;
     int nb = vhr_band_bins(T, fps, f_lo, f_hi, &k0, &k1);
     if (nb <= 0) {   // empty band: the filter output is identically zero
@@ -501,8 +511,11 @@ extern "C" int vhr_temporal_bandpass(vhr_ctx* ctx, const float* d_in, float* d_o
                 sub /= radices[i];
             }
             fa.pair_ok = (P % 2 == 0) && ((reinterpret_cast<uintptr_t>(d_in) & 7) == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 7) == 0);
-            // mask in digit-reversed (DIF output) order; cached per (T, band, gain)
-            if (!(ctx->mask && ctx->mask_T == T && ctx->mask_k0 == k0 && ctx->mask_k1 == k1 && ctx->mask_gain == gain)) {
+            // mask in digit-reversed (DIF output) order; cached per (T, band, gain, pass order)
+            unsigned long long rkey = 1;
+            for (int r : radices) rkey = rkey * 16ull + (unsigned long long)r;
+            if (!(ctx->mask && ctx->mask_T == T && ctx->mask_k0 == k0 && ctx->mask_k1 == k1 && ctx->mask_gain == gain &&
+                  ctx->mask_radix_key == rkey)) {
                 std::vector<float> hm((size_t)T);
                 const float g = (float)((double)gain / (double)T);
                 for (int pos = 0; pos < T; ++pos) {
@@ -520,7 +533,7 @@ extern "C" int vhr_temporal_bandpass(vhr_ctx* ctx, const float* d_in, float* d_o
                 VHR_CHECK_CUDA(ctx, cudaStreamSynchronize(stream));      // previous users of the cached mask
                 VHR_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->mask, hm.data(), sizeof(float) * (size_t)T, cudaMemcpyHostToDevice, stream));
                 VHR_CHECK_CUDA(ctx, cudaStreamSynchronize(stream));
-                ctx->mask_T = T; ctx->mask_k0 = k0; ctx->mask_k1 = k1; ctx->mask_gain = gain;
+                ctx->mask_T = T; ctx->mask_k0 = k0; ctx->mask_k1 = k1; ctx->mask_gain = gain; ctx->mask_radix_key = rkey;
             }
             fa.mask = ctx->mask;
             VHR_CHECK_CUDA(ctx, cudaFuncSetAttribute(bandpass_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));

@@ -119,7 +119,7 @@ __device__ ArgMax block_argmax(ArgMax a, ArgMax* sh) {
 
 struct FftArgs {
     const double* trace;
-    int n_trace, C;
+    int n_trace, C, ld, cs;
     const int32_t* start;
     const int32_t* len;
     double fs, f_lo, f_hi;
@@ -147,24 +147,31 @@ __global__ void __launch_bounds__(BT) bpm_fft_kernel(const FftArgs a) {
         sincospi(2.0 * (double)m / (double)n, &sv, &cv);
         tw[m] = make_double2(cv, sv);
     }
-    // positive-frequency bins 1..(n-1)/2 (freqs > 0 in fftfreq order), inclusive band
-    const int kmax = (n - 1) / 2;
+    // positive-frequency bins 1..(n-1)/2 (freqs > 0 in fftfreq order), inclusive band.  The VIDEO
+    // estimator masks the SIGNED fftfreq grid (rppg_VIDEO.py:137-140): with f_lo <= 0 the DC bin and
+    // the negative-frequency bins (n-1)/2+1 .. n-1 are candidates too.
+    const bool all_bins = a.mode == VHR_FFT_VIDEO && !(a.f_lo > 0.0);
+    const int kpos = (n - 1) / 2;
+    const int kmin = all_bins ? 0 : 1;
+    const int kmax = all_bins ? n - 1 : kpos;
     ArgMax best;
     best.v = 0.;
     best.k = -1;
     for (int c = 0; c < a.C; ++c) {
         __syncthreads();
-        for (int i = threadIdx.x; i < n; i += BT) x[i] = a.trace[(size_t)(s + i) * a.C + c];
+        for (int i = threadIdx.x; i < n; i += BT) x[i] = a.trace[(size_t)(s + i) * a.ld + (size_t)c * a.cs];
         __syncthreads();
         detrend_window(x, xf, n, a.detrend);
         ArgMax mine;
         mine.v = 0.;
         mine.k = -1;
         // one warp per bin (long windows: a single window must not serialise 1800 samples per thread)
-        for (int k = 1 + (int)(threadIdx.x >> 5); k <= kmax; k += BT / 32) {
-            const double f = np_freq(k, n, a.fs);
+        for (int k = kmin + (int)(threadIdx.x >> 5); k <= kmax; k += BT / 32) {
+            const double f = np_freq(k <= kpos ? k : k - n, n, a.fs);
             if (f >= a.f_lo && f <= a.f_hi) {           // warp-uniform
-                const double p = dft_power_warp(x, n, k, tw);
+                // a negative-frequency bin has the magnitude of its mirror n - k (real input; NumPy's fft of a
+                // real array mirrors it exactly), so ties between the two resolve to the lower index as in np.argmax
+                const double p = dft_power_warp(x, n, k <= kpos ? k : n - k, tw);
                 if (mine.k < 0 || p > mine.v) { mine.v = p; mine.k = k; }
             }
         }
@@ -174,7 +181,7 @@ __global__ void __launch_bounds__(BT) bpm_fft_kernel(const FftArgs a) {
     }
     if (threadIdx.x == 0) {
         if (best.k < 0) { a.bpm[w] = qnan(); a.bin[w] = -1; }
-        else { a.bpm[w] = __dmul_rn(np_freq(best.k, n, a.fs), 60.0); a.bin[w] = best.k; }
+        else { a.bpm[w] = __dmul_rn(np_freq(best.k <= kpos ? best.k : best.k - n, n, a.fs), 60.0); a.bin[w] = best.k; }
     }
 }
 
@@ -314,11 +321,14 @@ __global__ void __launch_bounds__(BT) bpm_welch_kernel(const __grid_constant__ W
             a.filtered[(size_t)w * a.max_len + i] = (i < n) ? x[i] : qnan();
 
     // estimate_bpm_welch: float32 cast, minus nanmean (float32), then welch in float64 here
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < n; ++i) xf[i] = (float)x[i];
-        const float m = __fdiv_rn(pairwise_sum_f32(xf, n), (float)n);
-        for (int i = 0; i < n; ++i) x[i] = (double)__fsub_rn(xf[i], m);
-    }
+    // (the float32 copy goes to xf; x is rewritten only after every thread has stored its part of
+    // `filtered` above and has read the shared mean)
+    __shared__ float welch_mean;
+    for (int i = threadIdx.x; i < n; i += BT) xf[i] = (float)x[i];
+    __syncthreads();
+    if (threadIdx.x == 0) welch_mean = __fdiv_rn(pairwise_sum_f32(xf, n), (float)n);      // NumPy's pairwise order
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += BT) x[i] = (double)__fsub_rn(xf[i], welch_mean);
     int nperseg = (int)fmin((double)n, __dmul_rn(a.fs, a.welch_seconds));     // int(min(len(x), fps*9))
     if (nperseg < 1) nperseg = 1;
     const int noverlap = nperseg / 2;
@@ -406,17 +416,17 @@ static int check_windows(vhr_ctx* ctx, int n_trace, int n_win) {
     return VHR_OK;
 }
 
-extern "C" int vhr_bpm_fft(vhr_ctx* ctx, const double* d_trace, int n_trace, int C, const int32_t* d_start,
+extern "C" int vhr_bpm_fft(vhr_ctx* ctx, const double* d_trace, int n_trace, int C, int ld, int cs, const int32_t* d_start,
                            const int32_t* d_len, int n_win, int max_len, double fs, double f_lo, double f_hi,
                            int detrend, int mode, double* d_bpm, int32_t* d_bin, void* stream) {
     VHR_REQUIRE(ctx, ctx != nullptr, "null context");
     VHR_REQUIRE(ctx, d_trace && d_start && d_len && d_bpm && d_bin, "null pointer");
-    VHR_REQUIRE(ctx, C >= 1 && fs > 0, "bad arguments");
+    VHR_REQUIRE(ctx, C >= 1 && cs >= 1 && ld >= 1 && fs > 0, "bad arguments");
     VHR_REQUIRE(ctx, detrend >= 0 && detrend <= 3 && (mode == 0 || mode == 1), "bad detrend/mode");
     int rc = check_windows(ctx, n_trace, n_win);
     if (rc != VHR_OK) return rc;
     FftArgs a;
-    a.trace = d_trace; a.n_trace = n_trace; a.C = C; a.start = d_start; a.len = d_len;
+    a.trace = d_trace; a.n_trace = n_trace; a.C = C; a.ld = ld; a.cs = cs; a.start = d_start; a.len = d_len;
     a.fs = fs; a.f_lo = f_lo; a.f_hi = f_hi; a.detrend = detrend; a.mode = mode; a.bpm = d_bpm; a.bin = d_bin;
     VHR_REQUIRE(ctx, max_len >= 1 && max_len <= n_trace, "max_len must be 1..n_trace");
     a.max_len = max_len;

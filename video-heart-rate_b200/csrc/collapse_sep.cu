@@ -27,6 +27,11 @@
 //     flight per warp; no barrier wider than a warp anywhere in the kernel;
 //   * ROI sums: per-lane float accumulators -> warp shuffle -> one double partial per item
 //     -> fixed-order finalize kernel.  No atomics: results are run-to-run identical.
+//     Rectangles are tested by coordinates; polygons (forehead / cheek outlines) are rasterised
+//     once per frame by poly_rowmask_kernel (roi.cu: the frozen exact-integer rule, one bit per
+//     pixel, frame-aligned 32-pixel words) and an item reads the 4 bits of its lane's pixels;
+//   * ROI-only calls (no frame output requested, the measurement plugins' case) retire every
+//     item that touches no ROI before it requests a single pixel.
 #include "common.cuh"
 #include <stdlib.h>
 #include <math.h>
@@ -55,8 +60,10 @@ struct SepArgs {
     const int* xb;            // (nsegs*32)  first level-L column per aligned 4-pixel group
     const float4* yw;         // (H) vertical weights per row
     const int* yb;            // (H) first level-L row per output row
-    const int32_t* rects;     // (T,K,4)
-    int K;
+    const int32_t* rects;     // ROI k of frame t at rects[(t * Kstride + k) * 4]: rectangle, or a polygon's clamped bounding box
+    int K, Kstride;
+    const uint32_t* mask;     // RM == 2: (T, K, H, MW) row bit-masks of the polygons (bit x & 31 of word x >> 5)
+    int MW;
     double* partial;          // (T, nbands, nsegs, K, 3)
 };
 
@@ -92,7 +99,8 @@ __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes
 
 // LOAD: 0 = scalar pixel loads (any W), 1 = 3 x LDG.32 per lane (W % 4 == 0),
 //       2 = one cp.async.bulk per warp row into a shared-memory ring (W % 16 == 0).
-template <int KMAX, bool F32OUT, bool U8OUT, int LOAD>
+// RM: 0 = no ROI, 1 = rectangles, 2 = polygon row masks.
+template <int KMAX, int RM, bool F32OUT, bool U8OUT, int LOAD>
 __global__ void __launch_bounds__(WARPS * 32, 2) collapse_sep_kernel(const SepArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr bool VEC = LOAD >= 1;
@@ -112,6 +120,28 @@ __global__ void __launch_bounds__(WARPS * 32, 2) collapse_sep_kernel(const SepAr
     const int y0 = band * a.BH, y1 = min(a.H, y0 + a.BH);
     const bool active = X < a.W;
     const int Xc = active ? X : X0;                    // address-safe column for idle lanes
+
+    // ROIs that intersect this item (rectangle, or bounding box of a polygon)
+    int rx1[KMAXF > 0 ? KMAXF : 1], ry1[KMAXF > 0 ? KMAXF : 1], rx2[KMAXF > 0 ? KMAXF : 1], ry2[KMAXF > 0 ? KMAXF : 1];
+    bool hit[KMAXF > 0 ? KMAXF : 1];
+    float acc[KMAXF > 0 ? KMAXF : 1][3];
+    bool any_hit = false;
+    if (KMAX > 0) {
+        const int xe = min(a.W, X0 + 128);
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            hit[k] = false;
+            acc[k][0] = acc[k][1] = acc[k][2] = 0.f;
+            if (k < a.K) {
+                const int32_t* rc = a.rects + ((size_t)t * a.Kstride + k) * 4;
+                rx1[k] = rc[0]; ry1[k] = rc[1]; rx2[k] = rc[2]; ry2[k] = rc[3];
+                hit[k] = rc[0] < xe && rc[2] > X0 && rc[1] < y1 && rc[3] > y0 && rc[2] > rc[0] && rc[3] > rc[1];
+                any_hit |= hit[k];
+            }
+        }
+    }
+    // ROI-only call: an item outside every ROI has nothing to produce (warp-uniform exit, before any pixel is requested)
+    if (!F32OUT && !U8OUT && !any_hit) return;
 
     // per-warp shared memory: NSTRIP output strips, then the pixel ring, then its barriers
     unsigned char* wsm = smem_raw + (size_t)warp * WARP_SMEM;
@@ -206,26 +236,6 @@ __global__ void __launch_bounds__(WARPS * 32, 2) collapse_sep_kernel(const SepAr
     float Wn[4][12];
     hx_row(cur, Wn[0]); hx_row(cur + 1, Wn[1]); hx_row(cur + 2, Wn[2]); hx_row(cur + 3, Wn[3]);
     prefetch_lrow(cur + 4);
-
-    // ROI rectangles that intersect this item
-    int rx1[KMAXF > 0 ? KMAXF : 1], ry1[KMAXF > 0 ? KMAXF : 1], rx2[KMAXF > 0 ? KMAXF : 1], ry2[KMAXF > 0 ? KMAXF : 1];
-    bool hit[KMAXF > 0 ? KMAXF : 1];
-    float acc[KMAXF > 0 ? KMAXF : 1][3];
-    bool any_hit = false;
-    if (KMAX > 0) {
-        const int xe = min(a.W, X0 + 128);
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-            hit[k] = false;
-            acc[k][0] = acc[k][1] = acc[k][2] = 0.f;
-            if (k < a.K) {
-                const int32_t* rc = a.rects + ((size_t)t * a.K + k) * 4;
-                rx1[k] = rc[0]; ry1[k] = rc[1]; rx2[k] = rc[2]; ry2[k] = rc[3];
-                hit[k] = rc[0] < xe && rc[2] > X0 && rc[1] < y1 && rc[3] > y0 && rc[2] > rc[0] && rc[3] > rc[1];
-                any_hit |= hit[k];
-            }
-        }
-    }
 
     const uint32_t nbytes = (uint32_t)min(32, (a.W - X0) >> 2) * 48;          // VEC: W % 4 == 0
     float* owarp = F32OUT ? a.out_f32 + (((size_t)t * a.H + y0) * a.W + X0) * 3 : nullptr;   // warp-uniform, this row
@@ -325,10 +335,25 @@ __global__ void __launch_bounds__(WARPS * 32, 2) collapse_sep_kernel(const SepAr
 #pragma unroll
             for (int k = 0; k < KMAX; ++k) {
                 if (hit[k] && y >= ry1[k] && y < ry2[k]) {
+                    if (RM == 2) {
+                        // 4 mask bits of this lane's pixels (X % 4 == 0: they never straddle a word); only the
+                        // words of the bounding box were written, lanes outside it do not read
+                        if (X + 4 > rx1[k] && X < rx2[k]) {
+                            const uint32_t mw = __ldg(a.mask + (((size_t)t * a.Kstride + k) * a.H + y) * a.MW + (X >> 5));
+                            const uint32_t bits = (mw >> (X & 31)) & 0xFu;
 #pragma unroll
-                    for (int px = 0; px < 4; ++px) {
-                        if (X + px >= rx1[k] && X + px < rx2[k] && X + px < a.W) {
-                            acc[k][0] += o[3 * px]; acc[k][1] += o[3 * px + 1]; acc[k][2] += o[3 * px + 2];
+                            for (int px = 0; px < 4; ++px) {
+                                if ((bits >> px) & 1u) {
+                                    acc[k][0] += o[3 * px]; acc[k][1] += o[3 * px + 1]; acc[k][2] += o[3 * px + 2];
+                                }
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int px = 0; px < 4; ++px) {
+                            if (X + px >= rx1[k] && X + px < rx2[k] && X + px < a.W) {
+                                acc[k][0] += o[3 * px]; acc[k][1] += o[3 * px + 1]; acc[k][2] += o[3 * px + 2];
+                            }
                         }
                     }
                 }
@@ -352,23 +377,28 @@ __global__ void __launch_bounds__(WARPS * 32, 2) collapse_sep_kernel(const SepAr
     }
 }
 
-// fixed-order reduction of the per-item partials over the items a rectangle touches
-__global__ void roi_finalize_sep_kernel(const double* __restrict__ partial, const int32_t* __restrict__ rects,
-                                        int T, int K, int BH, int nbands, int nsegs, double* __restrict__ mean) {
+// fixed-order reduction of the per-item partials over the items a ROI's rectangle / bounding box touches.
+// Rectangles outside the frame give NaN (like rect_mean_u8_kernel: the caller is expected to have applied
+// NumPy slice semantics, host.slice_rects); polygons divide by their rasterised pixel count.
+__global__ void roi_finalize_sep_kernel(const double* __restrict__ partial, const int32_t* __restrict__ rects, int Kstride,
+                                        const long long* __restrict__ count, int T, int K, int H, int W, int BH, int nbands,
+                                        int nsegs, double* __restrict__ mean) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= T * K * 3) return;
     const int c = idx % 3, k = (idx / 3) % K, t = idx / (3 * K);
-    const int32_t* rc = rects + ((size_t)t * K + k) * 4;
+    const int32_t* rc = rects + ((size_t)t * Kstride + k) * 4;
     const int x1 = rc[0], y1 = rc[1], x2 = rc[2], y2 = rc[3];
-    if (x2 <= x1 || y2 <= y1) {
-        mean[idx] = __longlong_as_double(0x7FF8000000000000ll);   // NaN, like np.mean of an empty slice
+    double* out = mean + ((size_t)t * Kstride + k) * 3 + c;
+    const long long n = count ? count[(size_t)t * Kstride + k] : (long long)(x2 - x1) * (long long)(y2 - y1);
+    if (x2 <= x1 || y2 <= y1 || x1 < 0 || y1 < 0 || x2 > W || y2 > H || n <= 0) {
+        *out = __longlong_as_double(0x7FF8000000000000ll);   // NaN, like np.mean of an empty slice
         return;
     }
     double s = 0.0;
     for (int b = y1 / BH; b <= (y2 - 1) / BH && b < nbands; ++b)
         for (int sg = x1 / 128; sg <= (x2 - 1) / 128 && sg < nsegs; ++sg)
             s += partial[((((size_t)t * nbands + b) * nsegs + sg) * K + k) * 3 + c];
-    mean[idx] = s / ((double)(x2 - x1) * (double)(y2 - y1));
+    *out = s / (double)n;
 }
 
 // ---- host: compose `levels` pyrUp steps along one axis into a banded matrix ---------------
@@ -429,13 +459,13 @@ bool make_tables(int n0, int levels, int group, int n_pad, std::vector<float>& w
     return true;
 }
 
-template <int KMAX>
+template <int KMAX, int RM>
 int launch_sep(vhr_ctx* ctx, const SepArgs& a, int load, cudaStream_t stream) {
     const unsigned grid = (unsigned)((a.n_items + WARPS - 1) / WARPS);
     const size_t smem = (size_t)WARPS * WARP_SMEM;
 #define VHR_SEP_LAUNCH(F, U, V)                                                                               \
     do {                                                                                                      \
-        auto kern = collapse_sep_kernel<KMAX, F, U, V>;                                                       \
+        auto kern = collapse_sep_kernel<KMAX, RM, F, U, V>;                                                   \
         VHR_CHECK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         kern<<<grid, WARPS * 32, smem, stream>>>(a);                                                          \
     } while (0)
@@ -452,11 +482,18 @@ int launch_sep(vhr_ctx* ctx, const SepArgs& a, int load, cudaStream_t stream) {
     return vhr_after_launch(ctx, "collapse_sep_kernel");
 }
 
-}  // namespace
+struct RoiSpec {                 // one fused-ROI request
+    const int32_t* rects;        // (T,K,4) rectangles, or NULL when polygons are given
+    const int32_t* poly;         // (T,K,Vmax,2)
+    const int32_t* nvert;        // (T,K)
+    int K, Vmax;
+    double* mean;                // (T,K,3)
+    int64_t* count;              // (T,K) polygons only, optional
+};
 
-int vhr_collapse_sep(vhr_ctx* ctx, const float* d_level, const uint8_t* d_frames, int T, int H, int W, int levels,
-                     float* d_out_f32, uint8_t* d_out_u8, const int32_t* d_rects, int K, double* d_roi_mean,
-                     cudaStream_t stream) {
+// Frames [0, T) of the pointers given; ROIs [k0, k0 + Kg) of `roi` (Kg <= KMAXF); frame outputs may be NULL.
+int collapse_group(vhr_ctx* ctx, const float* d_level, const uint8_t* d_frames, int T, int H, int W, int levels,
+                   float* d_out_f32, uint8_t* d_out_u8, const RoiSpec& roi, int k0, int Kg, cudaStream_t stream) {
     SepArgs a;
     memset(&a, 0, sizeof(a));
     a.lvl = d_level; a.frames = d_frames; a.out_f32 = d_out_f32; a.out_u8 = d_out_u8;
@@ -509,24 +546,106 @@ int vhr_collapse_sep(vhr_ctx* ctx, const float* d_level, const uint8_t* d_frames
     const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_frames) & 3) == 0) &&
                      (!d_out_f32 || (reinterpret_cast<uintptr_t>(d_out_f32) & 15) == 0) &&
                      (!d_out_u8 || (reinterpret_cast<uintptr_t>(d_out_u8) & 3) == 0);
-    a.rects = d_rects; a.K = K;
-    if (K > 0) {
-        void* p = nullptr;
-        int rc = vhr_scratch(ctx, sizeof(double) * (size_t)T * a.nbands * a.nsegs * K * 3, &p);
-        if (rc != VHR_OK) return rc;
-        a.partial = reinterpret_cast<double*>(p);
-    }
     int load = vec ? 1 : 0;
     if (vec && W % 16 == 0 && (reinterpret_cast<uintptr_t>(d_frames) & 15) == 0) load = 2;
     if (const char* e = getenv("VHR_COLLAPSE_LOAD")) { const int v = atoi(e); if (v >= 0 && v < load) load = v; }
-    int rc = (K == 0) ? launch_sep<0>(ctx, a, load, stream)
-           : (K == 1) ? launch_sep<1>(ctx, a, load, stream)
-                      : launch_sep<KMAXF>(ctx, a, load, stream);
+
+    const bool poly = Kg > 0 && roi.poly != nullptr;
+    const int32_t* boxes = nullptr;       // rectangles or polygon bounding boxes of ROIs [k0, k0 + Kg), stride roi.K
+    const long long* counts = nullptr;
+    a.K = Kg; a.Kstride = roi.K;
+    if (Kg > 0) {
+        // scratch: [partials | polygon boxes (T,K,4) | polygon counts (T,K) | row masks (T,K,H,MW)]
+        auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+        const int Kp = roi.K < KMAXF ? roi.K : KMAXF;            // every group of a call uses the same layout
+        const size_t part_bytes = al(sizeof(double) * (size_t)T * a.nbands * a.nsegs * Kp * 3);
+        const int MW = (W + 31) / 32;
+        const size_t box_bytes = poly ? al(sizeof(int32_t) * 4 * (size_t)T * roi.K) : 0;
+        const size_t cnt_bytes = poly ? al(sizeof(long long) * (size_t)T * roi.K) : 0;
+        const size_t mask_bytes = poly ? al(sizeof(uint32_t) * (size_t)T * roi.K * H * MW) : 0;
+        void* p = nullptr;
+        int rc = vhr_scratch(ctx, part_bytes + box_bytes + cnt_bytes + mask_bytes, &p);
+        if (rc != VHR_OK) return rc;
+        char* base = reinterpret_cast<char*>(p);
+        a.partial = reinterpret_cast<double*>(base);
+        if (poly) {
+            int32_t* bx = reinterpret_cast<int32_t*>(base + part_bytes);
+            long long* cn = reinterpret_cast<long long*>(base + part_bytes + box_bytes);
+            uint32_t* mk = reinterpret_cast<uint32_t*>(base + part_bytes + box_bytes + cnt_bytes);
+            // rasterise every polygon of the call once (k0 == 0 call; later groups of the same call reuse the scratch)
+            if (k0 == 0) {
+                rc = vhr_poly_rowmask(ctx, T, H, W, roi.poly, roi.nvert, roi.K, roi.Vmax, mk, MW, bx, cn, stream);
+                if (rc != VHR_OK) return rc;
+            }
+            boxes = bx + 4 * k0; counts = cn + k0;
+            a.mask = mk + (size_t)k0 * H * MW; a.MW = MW;
+        } else {
+            boxes = roi.rects + 4 * k0;
+        }
+        a.rects = boxes;
+    }
+    int rc;
+    if (Kg == 0) rc = launch_sep<0, 0>(ctx, a, load, stream);
+    else if (!poly) rc = (Kg == 1) ? launch_sep<1, 1>(ctx, a, load, stream) : launch_sep<KMAXF, 1>(ctx, a, load, stream);
+    else rc = (Kg == 1) ? launch_sep<1, 2>(ctx, a, load, stream) : launch_sep<KMAXF, 2>(ctx, a, load, stream);
     if (rc != VHR_OK) return rc;
-    if (K > 0) {
-        const int n = T * K * 3;
-        roi_finalize_sep_kernel<<<(n + 127) / 128, 128, 0, stream>>>(a.partial, d_rects, T, K, a.BH, a.nbands, a.nsegs, d_roi_mean);
+    if (Kg > 0) {
+        const int n = T * Kg * 3;
+        roi_finalize_sep_kernel<<<(n + 127) / 128, 128, 0, stream>>>(a.partial, boxes, roi.K, counts, T, Kg, H, W, a.BH, a.nbands,
+                                                                    a.nsegs, roi.mean + 3 * k0);
         rc = vhr_after_launch(ctx, "roi_finalize_sep_kernel");
+        if (rc == VHR_OK && poly && roi.count && k0 + Kg >= roi.K) {
+            VHR_CHECK_CUDA(ctx, cudaMemcpyAsync(roi.count, counts - k0, sizeof(long long) * (size_t)T * roi.K, cudaMemcpyDeviceToDevice, stream));
+        }
     }
     return rc;
+}
+
+int collapse_impl(vhr_ctx* ctx, const float* d_level, const uint8_t* d_frames, int T, int H, int W, int levels,
+                  float* d_out_f32, uint8_t* d_out_u8, const RoiSpec& roi, cudaStream_t stream) {
+    VHR_REQUIRE(ctx, ctx != nullptr, "null context");
+    VHR_REQUIRE(ctx, d_level && d_frames, "null pointer");
+    VHR_REQUIRE(ctx, T >= 1 && H >= 1 && W >= 1, "bad shape");
+    VHR_REQUIRE(ctx, levels >= 1 && levels <= VHR_MAX_LEVELS, "levels must be 1..6");
+    VHR_REQUIRE(ctx, roi.K >= 0 && roi.K <= VHR_MAX_ROIS, "fused ROI count must be 0..8");
+    VHR_REQUIRE(ctx, roi.K == 0 || ((roi.rects || (roi.poly && roi.nvert)) && roi.mean), "ROI pointers missing");
+    VHR_REQUIRE(ctx, !roi.poly || (roi.Vmax >= 1 && roi.Vmax <= VHR_MAX_POLY_VERTS), "Vmax must be 1..64");
+    VHR_REQUIRE(ctx, !roi.poly || W <= 8192, "polygon ROIs: frames up to 8192 pixels wide");
+    VHR_REQUIRE(ctx, d_out_f32 || d_out_u8 || roi.K > 0, "nothing to compute");
+    int rc = vhr_enter(ctx, stream);       // composite tables + scratch arena are context-owned
+    if (rc != VHR_OK) return rc;
+    // ROIs in groups of KMAXF: the first group rides on the frame-output pass, the others are ROI-only passes
+    // (items outside their ROIs retire at once).  All groups share one scratch layout, so a later group must not
+    // start before the previous finalize has read its partials: same stream, in order.
+    int k0 = 0;
+    do {
+        const int Kg = roi.K - k0 < KMAXF ? roi.K - k0 : KMAXF;
+        rc = collapse_group(ctx, d_level, d_frames, T, H, W, levels, k0 == 0 ? d_out_f32 : nullptr, k0 == 0 ? d_out_u8 : nullptr,
+                            roi, k0, Kg, stream);
+        k0 += KMAXF;
+    } while (rc == VHR_OK && k0 < roi.K);
+    return vhr_leave(ctx, stream, rc);
+}
+
+}  // namespace
+
+extern "C" int vhr_collapse_addback_roi(vhr_ctx* ctx, const float* d_level, const uint8_t* d_frames, int T, int H, int W,
+                                        int levels, float* d_out_f32, uint8_t* d_out_u8, const int32_t* d_rects, int K,
+                                        double* d_roi_mean, void* stream) {
+    RoiSpec roi;
+    memset(&roi, 0, sizeof(roi));
+    roi.rects = d_rects; roi.K = K; roi.mean = d_roi_mean;
+    if (ctx && K > 0 && !d_rects) { vhr_set_error(ctx, "vhr_collapse_addback_roi: ROI pointers missing"); return VHR_ERR_INVALID; }
+    return collapse_impl(ctx, d_level, d_frames, T, H, W, levels, d_out_f32, d_out_u8, roi, (cudaStream_t)stream);
+}
+
+extern "C" int vhr_collapse_addback_poly(vhr_ctx* ctx, const float* d_level, const uint8_t* d_frames, int T, int H, int W,
+                                         int levels, float* d_out_f32, uint8_t* d_out_u8, const int32_t* d_poly,
+                                         const int32_t* d_nvert, int K, int Vmax, double* d_roi_mean, int64_t* d_count,
+                                         void* stream) {
+    RoiSpec roi;
+    memset(&roi, 0, sizeof(roi));
+    roi.poly = d_poly; roi.nvert = d_nvert; roi.K = K; roi.Vmax = Vmax; roi.mean = d_roi_mean; roi.count = d_count;
+    if (ctx && (K < 1 || !d_poly || !d_nvert)) { vhr_set_error(ctx, "vhr_collapse_addback_poly: polygon pointers missing"); return VHR_ERR_INVALID; }
+    return collapse_impl(ctx, d_level, d_frames, T, H, W, levels, d_out_f32, d_out_u8, roi, (cudaStream_t)stream);
 }

@@ -23,9 +23,16 @@ struct vhr_ctx {
     float* mask = nullptr;
     int mask_T = 0, mask_k0 = -1, mask_k1 = -1;
     float mask_gain = 0.f;
+    unsigned long long mask_radix_key = 0;    // pass order of the FFT the mask's digit-reversed layout belongs to
+    // stream hand-over (vhr_enter / vhr_leave): the cached tables and the scratch arena are shared by every
+    // call of a context, so a call on another stream than the previous one first waits for that one
+    cudaStream_t last_stream = nullptr;
+    cudaEvent_t last_ev = nullptr;
+    bool have_last = false;
     // context-owned buffers of the *_host convenience path
     void* hostpath = nullptr;
     size_t hostpath_bytes = 0;
+    cudaStream_t hp_copy = nullptr, hp_comp = nullptr;     // created on first use, destroyed with the context
     // composite pyrUp weight tables of the collapse (collapse_sep.cu), keyed by shape
     void* sep_tab = nullptr;
     size_t sep_tab_bytes = 0;
@@ -33,11 +40,19 @@ struct vhr_ctx {
 };
 
 void vhr_set_error(vhr_ctx* ctx, const char* fmt, ...);
+// Contract: a context is used by ONE stream at a time.  Entry points that read or rewrite context-owned
+// device state (twiddles, band mask, composite pyrUp tables, scratch arena) bracket their work with
+// vhr_enter / vhr_leave: when the stream differs from the previous call's, the new stream first waits
+// for the previous call's work, so switching streams between calls is safe; two streams driving one
+// context concurrently is not supported.
+int vhr_enter(vhr_ctx* ctx, cudaStream_t stream);
+int vhr_leave(vhr_ctx* ctx, cudaStream_t stream, int rc);
 int vhr_scratch(vhr_ctx* ctx, size_t bytes, void** out);
-// collapse_sep.cu: separable-composite collapse (arguments as vhr_collapse_addback_roi, validated by the caller)
-int vhr_collapse_sep(vhr_ctx* ctx, const float* d_level, const uint8_t* d_frames, int T, int H, int W, int levels,
-                     float* d_out_f32, uint8_t* d_out_u8, const int32_t* d_rects, int K, double* d_roi_mean,
-                     cudaStream_t stream);
+// roi.cu: rasterise polygons (T,K,Vmax,2) into frame-aligned row bit-masks (T,K,H,MW) (only the rows and
+// words of each polygon's clamped bounding box are written), their bounding boxes (T,K,4) [x1,y1,x2,y2)
+// (all zero when empty) and pixel counts (T,K).  Used by the fused polygon ROI of the collapse.
+int vhr_poly_rowmask(vhr_ctx* ctx, int T, int H, int W, const int32_t* d_poly, const int32_t* d_nvert, int K, int Vmax,
+                     uint32_t* d_mask, int MW, int32_t* d_box, long long* d_count, cudaStream_t stream);
 
 #define VHR_CHECK_CUDA(ctx, expr)                                                        \
     do {                                                                                 \

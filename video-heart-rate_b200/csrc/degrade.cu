@@ -2,9 +2,10 @@
 //
 //   vhr_degrade_noise_u8     analysis/degradation/colour_noise.py:11-24 (add_gaussian_noise):
 //                            clip(float32(frame) + noise, 0, 255).astype(uint8)  [astype truncates]
-//                            The reference draws np.random.normal; here the noise is the same
-//                            counter-based hash as the synthetic generator (sum of four hash bytes,
-//                            std = sigma), so the CPU oracle reproduces it bit for bit.
+//                            The reference draws np.random.normal; here the draw is a 12-term
+//                            Irwin-Hall sum (twelve hash bytes of three counter-based words; mean 0,
+//                            std sigma, tails to +-5.98 sigma, excess kurtosis -0.1) -- pure integer
+//                            arithmetic, so the CPU oracle reproduces it bit for bit.
 //   vhr_degrade_quantise_u8  analysis/degradation/colour_quantisation.py:12-25 (quantise_colour):
 //                            scale = 256 // 2**bits ; (frame // scale) * scale  (scale == 0, i.e.
 //                            bits > 8, gives 0 like NumPy's uint8 // 0)
@@ -34,9 +35,13 @@ __global__ void __launch_bounds__(256) noise_kernel(const uint8_t* __restrict__ 
             const unsigned t = (unsigned)(g / frame_bytes);
             const uint32_t idx = (uint32_t)(g - (long long)t * frame_bytes);
             const uint32_t key = dmix32(seed * 0x9E3779B1u + clip * 0x85EBCA77u + (uint32_t)(t0 + (int)t) * 0xC2B2AE3Du + 0x3C6EF372u);
-            const uint32_t r = dmix32(key ^ (idx * 0x27D4EB2Fu));
-            const int s = (int)((r & 255u) + ((r >> 8) & 255u) + ((r >> 16) & 255u) + (r >> 24)) - 510;
-            int v = ((int)in[g] * 256 + s * gain) >> 8;           // floor((x + noise)) ; astype(uint8) truncates
+            int s = -1530;                                        // twelve bytes: mean 1530, std sqrt(65535) = 255.998
+#pragma unroll
+            for (uint32_t w = 0; w < 3; ++w) {
+                const uint32_t r = dmix32((key + w * 0x9E3779B9u) ^ (idx * 0x27D4EB2Fu));
+                s += (int)__dp4a(r, 0x01010101u, 0u);
+            }
+            int v = ((int)in[g] * 65536 + s * gain) >> 16;        // floor(x + noise); clip, then astype(uint8) truncates
             v = min(max(v, 0), 255);
             word |= (uint32_t)v << (8 * j);
         }
@@ -82,16 +87,17 @@ __global__ void mean_kernel(const double* __restrict__ x, int m, double* __restr
 }  // namespace
 
 extern "C" int vhr_degrade_noise_u8(vhr_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int T, int H, int W,
-                                    int noise_gain_q8, uint32_t seed, uint32_t clip, int t0, void* stream) {
+                                    int noise_gain_q16, uint32_t seed, uint32_t clip, int t0, void* stream) {
     VHR_REQUIRE(ctx, ctx != nullptr, "null context");
     VHR_REQUIRE(ctx, d_in && d_out, "null pointer");
     VHR_REQUIRE(ctx, T >= 1 && H >= 1 && W >= 1, "bad shape");
     VHR_REQUIRE(ctx, (long long)H * W * 3 < 0xFFFFFFFFll, "frame too large");
+    VHR_REQUIRE(ctx, noise_gain_q16 >= 0 && noise_gain_q16 <= 1000000, "noise gain out of range (sigma <= 3900 LSB)");
     const long long total = (long long)T * H * W * 3;
     long long blocks = (total / 4 + 255) / 256;
     if (blocks > ctx->num_sms * 32) blocks = ctx->num_sms * 32;
     if (blocks < 1) blocks = 1;
-    noise_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_in, d_out, total, (unsigned)(H * W * 3), seed, clip, t0, noise_gain_q8);
+    noise_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_in, d_out, total, (unsigned)(H * W * 3), seed, clip, t0, noise_gain_q16);
     return vhr_after_launch(ctx, "noise_kernel");
 }
 

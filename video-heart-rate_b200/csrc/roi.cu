@@ -369,6 +369,57 @@ __global__ void __launch_bounds__(RT) poly_mean_scan_kernel(const Tpix* __restri
     }
 }
 
+// Row bit-masks of every polygon for the fused ROI of the collapse (collapse_sep.cu): the same
+// scan_row_mask rows, laid out on frame-aligned words (bit x & 31 of word x >> 5) so that a collapse
+// lane finds the 4 bits of its 4 pixels in one word.  Only the bounding box is written.
+__global__ void __launch_bounds__(RT) poly_rowmask_kernel(int H, int W, const int32_t* __restrict__ poly,
+                                                           const int32_t* __restrict__ nvert, int K, int Vmax,
+                                                           uint32_t* __restrict__ mask, int MW, int32_t* __restrict__ box,
+                                                           long long* __restrict__ count) {
+    __shared__ int2 verts[VHR_MAX_POLY_VERTS];
+    __shared__ uint32_t rowmask[RT / 32][2][SCAN_MAXW];
+    __shared__ unsigned long long shu[RT / 32];
+    const int tk = blockIdx.x;
+    int n = nvert[tk];
+    n = min(max(n, 0), min(Vmax, VHR_MAX_POLY_VERTS));
+    const int32_t* pv = poly + ((size_t)tk * Vmax) * 2;
+    for (int i = threadIdx.x; i < n; i += RT) verts[i] = make_int2(pv[2 * i], pv[2 * i + 1]);
+    __syncthreads();
+    int bx0 = W, by0 = H, bx1 = -1, by1 = -1;
+    for (int i = 0; i < n; ++i) {
+        bx0 = min(bx0, verts[i].x); bx1 = max(bx1, verts[i].x);
+        by0 = min(by0, verts[i].y); by1 = max(by1, verts[i].y);
+    }
+    bx0 = max(bx0, 0); by0 = max(by0, 0); bx1 = min(bx1, W - 1); by1 = min(by1, H - 1);
+    const bool some = n > 0 && bx1 >= bx0 && by1 >= by0;
+    unsigned long long cnt = 0;
+    if (some) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int ax0 = bx0 & ~31;                                   // word-aligned origin of the row masks
+        const int bw = bx1 - ax0 + 1;
+        const int nw = (bw + 31) >> 5;
+        uint32_t* tog = rowmask[warp][0];
+        uint32_t* edg = rowmask[warp][1];
+        uint32_t* dst = mask + (size_t)tk * H * MW + (ax0 >> 5);
+        for (int y = by0 + warp; y <= by1; y += RT / 32) {
+            scan_row_mask(y, verts, n, ax0, bw, tog, edg);
+            for (int w = lane; w < nw; w += 32) {
+                const uint32_t m = tog[w];
+                dst[(size_t)y * MW + w] = m;
+                cnt += __popc(m);
+            }
+            __syncwarp();
+        }
+    }
+    const unsigned long long ctot = block_sum(cnt, shu);
+    if (threadIdx.x == 0) {
+        int32_t* b = box + (size_t)tk * 4;
+        if (some && ctot > 0) { b[0] = bx0; b[1] = by0; b[2] = bx1 + 1; b[3] = by1 + 1; }
+        else { b[0] = b[1] = b[2] = b[3] = 0; }
+        count[tk] = (long long)ctot;
+    }
+}
+
 __global__ void __launch_bounds__(RT) poly_mask_kernel(int H, int W, const int32_t* __restrict__ poly,
                                                         const int32_t* __restrict__ nvert, int K, int Vmax,
                                                         uint8_t* __restrict__ mask) {
@@ -387,6 +438,13 @@ __global__ void __launch_bounds__(RT) poly_mask_kernel(int H, int W, const int32
 }
 
 }  // namespace
+
+int vhr_poly_rowmask(vhr_ctx* ctx, int T, int H, int W, const int32_t* d_poly, const int32_t* d_nvert, int K, int Vmax,
+                     uint32_t* d_mask, int MW, int32_t* d_box, long long* d_count, cudaStream_t stream) {
+    VHR_REQUIRE(ctx, W <= 32 * SCAN_MAXW && MW >= (W + 31) / 32, "frame too wide for the row masks");
+    poly_rowmask_kernel<<<(unsigned)((size_t)T * K), RT, 0, stream>>>(H, W, d_poly, d_nvert, K, Vmax, d_mask, MW, d_box, d_count);
+    return vhr_after_launch(ctx, "poly_rowmask_kernel");
+}
 
 extern "C" int vhr_roi_mean_rect_u8(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int W,
                                     const int32_t* d_rects, int K, const int32_t* d_paint, int NP,

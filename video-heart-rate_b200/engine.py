@@ -133,15 +133,29 @@ class Engine:
                     "vhr_temporal_bandpass")
         return out
 
-    def collapse(self, level, frames, levels: int, out_f32=True, out_u8=False, rects=None):
-        """-> (out_f32 | None, out_u8 | None, roi_mean (T,K,3) float64 | None).  ``out_f32`` /
-        ``out_u8`` may be True (allocate), False (skip) or a preallocated tensor."""
+    def collapse(self, level, frames, levels: int, out_f32=True, out_u8=False, rects=None, polys=None, nverts=None,
+                 want_counts: bool = False):
+        """-> (out_f32 | None, out_u8 | None, roi_mean (T,K,3) float64 | None[, counts (T,K) int64]).
+        ``out_f32`` / ``out_u8`` may be True (allocate), False (skip) or a preallocated tensor.
+        ROIs: ``rects`` (T,K,4) rectangles, or ``polys`` (T,K,Vmax,2) + ``nverts`` (T,K) landmark
+        polygons (rasterised by the frozen exact-integer rule).  With both outputs False only the
+        image parts under a ROI are evaluated (ROI-only mode)."""
         torch = _torch()
         T, H, W, _ = frames.shape
         o32 = torch.empty((T, H, W, 3), dtype=torch.float32, device=self.tdev) if out_f32 is True else (
             None if out_f32 is False else out_f32)
         o8 = torch.empty((T, H, W, 3), dtype=torch.uint8, device=self.tdev) if out_u8 is True else (
             None if out_u8 is False else out_u8)
+        if polys is not None:
+            assert rects is None, "give rectangles or polygons, not both"
+            p, nv, K, V = self._poly_args(polys, nverts, T)
+            means = torch.empty((T, K, 3), dtype=torch.float64, device=self.tdev)
+            counts = torch.empty((T, K), dtype=torch.int64, device=self.tdev) if want_counts else None
+            self._check(self.lib.vhr_collapse_addback_poly(self.ctx, self._p(level), self._p(frames), T, H, W, levels,
+                                                           self._p(o32), self._p(o8), self._p(p), self._p(nv), K, V,
+                                                           self._p(means), self._p(counts), self._stream()),
+                        "vhr_collapse_addback_poly")
+            return (o32, o8, means, counts) if want_counts else (o32, o8, means)
         K, r_dev, means = 0, None, None
         if rects is not None:
             r_dev = self._dev(rects, torch.int32).reshape(T, -1, 4)
@@ -150,36 +164,61 @@ class Engine:
         self._check(self.lib.vhr_collapse_addback_roi(self.ctx, self._p(level), self._p(frames), T, H, W, levels,
                                                       self._p(o32), self._p(o8), self._p(r_dev), K, self._p(means),
                                                       self._stream()), "vhr_collapse_addback_roi")
-        return o32, o8, means
+        return (o32, o8, means, None) if want_counts else (o32, o8, means)
 
     def evm(self, frames, fps: float, levels: int = 4, f_lo: float = 0.7, f_hi: float = 4.0, alpha: float = 50.0,
-            rects=None, out_f32=True, out_u8=False, keep_levels: bool = False):
+            rects=None, out_f32=True, out_u8=False, keep_levels: bool = False, polys=None, nverts=None):
         """Whole EVM path on device-resident frames: pyrDown cascade -> ideal bandpass (x alpha)
-        -> collapse + add-back (+ fused rectangle ROI means)."""
+        -> collapse + add-back (+ fused rectangle / polygon ROI means)."""
         lvl = self.pyrdown(frames, levels)
         filt = self.bandpass(lvl, fps, f_lo, f_hi, alpha, out=None if keep_levels else lvl)
-        o32, o8, means = self.collapse(filt, frames, levels, out_f32=out_f32, out_u8=out_u8, rects=rects)
+        o32, o8, means, counts = self.collapse(filt, frames, levels, out_f32=out_f32, out_u8=out_u8, rects=rects,
+                                               polys=polys, nverts=nverts, want_counts=True)
         return {"level": lvl if keep_levels else None, "filtered": filt, "out_f32": o32, "out_u8": o8,
-                "roi_mean": means}
+                "roi_mean": means, "roi_count": counts}
 
-    def evm_roi_host(self, frames_np: np.ndarray, fps: float, rects_np: np.ndarray, levels: int = 4,
-                     f_lo: float = 0.7, f_hi: float = 4.0, alpha: float = 50.0, out: Optional[np.ndarray] = None):
-        """Host-buffer call (NumPy in, NumPy out): (T,H,W,3) uint8 -> (T,K,3) float64 ROI means.
-        H2D and D2H are inside the call (vhr_evm_roi_host)."""
+    def evm_roi_host(self, frames_np: np.ndarray, fps: float, rects_np: Optional[np.ndarray] = None, levels: int = 4,
+                     f_lo: float = 0.7, f_hi: float = 4.0, alpha: float = 50.0, out: Optional[np.ndarray] = None,
+                     polys_np: Optional[np.ndarray] = None, nverts_np: Optional[np.ndarray] = None,
+                     want_counts: bool = False):
+        """Host-buffer call (NumPy in, NumPy out): (T,H,W,3) uint8 -> (T,K,3) float64 ROI means
+        (and (T,K) int64 mask pixel counts with ``want_counts`` for polygons).  H2D and D2H are
+        inside the call (vhr_evm_roi_host / vhr_evm_poly_host).  ``frames_np`` should be
+        page-locked (e.g. ``torch.empty(..., pin_memory=True).numpy()``); pageable memory works
+        but its copies do not overlap the kernels.  Without ``out`` the magnified frames are
+        never materialised (ROI-only collapse)."""
         assert frames_np.dtype == np.uint8 and frames_np.flags.c_contiguous and frames_np.ndim == 4
         T, H, W, _ = frames_np.shape
-        rects_np = np.ascontiguousarray(rects_np, dtype=np.int32).reshape(T, -1, 4)
-        K = rects_np.shape[1]
-        means = np.empty((T, K, 3), dtype=np.float64)
         optr = C.c_void_p(0)
         if out is not None:
             assert out.dtype == np.float32 and out.flags.c_contiguous and out.shape == frames_np.shape
             optr = C.c_void_p(out.ctypes.data)
+        if polys_np is not None:
+            polys_np = np.ascontiguousarray(polys_np, dtype=np.int32)
+            assert polys_np.ndim == 4 and polys_np.shape[0] == T and polys_np.shape[3] == 2
+            K, V = polys_np.shape[1], polys_np.shape[2]
+            nverts_np = np.ascontiguousarray(nverts_np, dtype=np.int32).reshape(T, K)
+            means = np.empty((T, K, 3), dtype=np.float64)
+            counts = np.empty((T, K), dtype=np.int64) if want_counts else None
+            self._check(self.lib.vhr_evm_poly_host(self.ctx, C.c_void_p(frames_np.ctypes.data), T, H, W, levels,
+                                                   float(fps), float(f_lo), float(f_hi), float(alpha),
+                                                   C.c_void_p(polys_np.ctypes.data), C.c_void_p(nverts_np.ctypes.data), K, V,
+                                                   C.c_void_p(means.ctypes.data),
+                                                   C.c_void_p(counts.ctypes.data if want_counts else 0), optr),
+                        "vhr_evm_poly_host")
+            return (means, counts) if want_counts else means
+        rects_np = np.ascontiguousarray(rects_np, dtype=np.int32).reshape(T, -1, 4)
+        K = rects_np.shape[1]
+        means = np.empty((T, K, 3), dtype=np.float64)
         self._check(self.lib.vhr_evm_roi_host(self.ctx, C.c_void_p(frames_np.ctypes.data), T, H, W, levels,
                                               float(fps), float(f_lo), float(f_hi), float(alpha),
                                               C.c_void_p(rects_np.ctypes.data), K, C.c_void_p(means.ctypes.data),
                                               optr), "vhr_evm_roi_host")
-        return means
+        return (means, None) if want_counts else means
+
+    def trim(self):
+        """Release the context's cached device buffers (host-path arena, scratch arena)."""
+        self._check(self.lib.vhr_trim(self.ctx), "vhr_trim")
 
     # ------------------------------------------------------------------ ROI
     def roi_mean_rect(self, frames, rects, paint=None, paint_rgb=None):
@@ -233,12 +272,20 @@ class Engine:
     # ------------------------------------------------------------------ BPM
     def bpm_fft(self, trace, starts, lens, fs: float, band, detrend: int = DETREND_NONE, mode: int = FFT_ANALYSIS,
                 max_len: Optional[int] = None):
-        """trace float64 (n,) or (n,C); windows (start,len) -> (bpm float64 (n_win), bin int32)."""
+        """trace float64 (n,) or (n,C); windows (start,len) -> (bpm float64 (n_win), bin int32).
+        A device float64 VIEW (e.g. ``roi_mean[:, 0, 1]`` or ``roi_mean[:, :, 1]`` of a (T,K,3) trace) is
+        read in place through its row / column strides; with C > 1 columns the result is the peak of
+        the column with the largest peak (estimate_bpm.py:59-64)."""
         torch = _torch()
-        tr = self._dev(trace, torch.float64)
-        if tr.ndim == 1:
-            tr = tr[:, None].contiguous()
-        n, Cc = tr.shape
+        tr = trace
+        if not (isinstance(tr, torch.Tensor) and tr.is_cuda and tr.dtype == torch.float64 and tr.ndim in (1, 2)
+                and tr.shape[0] >= 1 and all(st_ >= 1 for st_ in tr.stride())):
+            tr = self._dev(trace, torch.float64)
+            if tr.ndim == 1:
+                tr = tr[:, None].contiguous()
+        n, Cc = tr.shape[0], (1 if tr.ndim == 1 else tr.shape[1])
+        ld = int(tr.stride(0)) if n > 1 else Cc
+        cs = int(tr.stride(1)) if (tr.ndim == 2 and Cc > 1) else 1
         st = self._dev(starts, torch.int32)
         ln = self._dev(lens, torch.int32)
         nw = st.numel()
@@ -250,7 +297,7 @@ class Engine:
             lens_np = np.asarray(lens if not isinstance(lens, torch.Tensor) else lens.cpu(), dtype=np.int64)
             max_len = int(lens_np.max())
         max_len = int(min(n, max(1, max_len)))
-        self._check(self.lib.vhr_bpm_fft(self.ctx, self._p(tr), n, Cc, self._p(st), self._p(ln), nw, max_len,
+        self._check(self.lib.vhr_bpm_fft(self.ctx, self._p(tr), n, Cc, ld, cs, self._p(st), self._p(ln), nw, max_len,
                                          float(fs), float(band[0]), float(band[1]), detrend, mode, self._p(bpm),
                                          self._p(kbin), self._stream()), "vhr_bpm_fft")
         return bpm, kbin
@@ -297,12 +344,13 @@ class Engine:
 
     # ------------------------------------------------------------------ degradations / metric
     def degrade_noise(self, frames, sigma: float, seed: int = 0, clip: int = 0, t0: int = 0, out=None):
-        """colour_noise.add_gaussian_noise on device (hash noise of std ``sigma`` LSB)."""
+        """colour_noise.add_gaussian_noise on device: counter-based 12-term Irwin-Hall draw of std
+        ``sigma`` LSB (tails to 5.98 sigma), clip, truncate (colour_noise.py:22-24)."""
         torch = _torch()
         assert frames.dtype == torch.uint8 and frames.is_cuda and frames.is_contiguous()
         T, H, W, _ = frames.shape
         out = torch.empty_like(frames) if out is None else out
-        gain = int(round(sigma * 256.0 / 147.80053225049948))
+        gain = int(round(sigma * 65536.0 / float(np.sqrt(65535.0))))      # Q16 per unit of the twelve-byte sum (std sqrt(65535))
         self._check(self.lib.vhr_degrade_noise_u8(self.ctx, self._p(frames), self._p(out), T, H, W, gain,
                                                   seed & 0xFFFFFFFF, clip & 0xFFFFFFFF, t0, self._stream()),
                     "vhr_degrade_noise_u8")

@@ -63,6 +63,84 @@ def cheek_roi_clamped(bb, w: int, h: int):
     return np.stack([rx1, ry1, rx2, ry2], 1)
 
 
+# ---------------------------------------------------------------------------------- polygons
+# The reference's ROIs are the ratio rectangles above (rppg_VIDEO.py:102-103); BASELINE.json's
+# north_star asks for landmark POLYGONS (forehead and cheeks).  Two sources of outlines:
+#   * ``ratio_polygons``     V-gons inscribed in the reference's own ratio rectangles of the landmark
+#                            bounding box (forehead; the cheek rectangle split into a left and a right
+#                            cheek); with ``shape="rect"`` the 4-gon IS the rectangle (same pixel set);
+#   * ``landmark_polygons``  outlines through chosen landmarks of the mesh (index lists).
+FACE_PARTS = (
+    # name, (horizontal_ratio, top_ratio, bottom_ratio) of rppg_VIDEO.py:102-103, (x_lo, x_hi) share of that rectangle
+    ("forehead", FOREHEAD, (0.0, 1.0)),
+    ("cheek_l", CHEEK, (0.0, 0.4)),
+    ("cheek_r", CHEEK, (0.6, 1.0)),
+)
+# MediaPipe FaceMesh outlines commonly used for rPPG (478-landmark topology).  mediapipe is not
+# installed in this image, so these lists could not be run against the reference's landmarker here.
+MESH_FOREHEAD = (109, 10, 338, 337, 336, 9, 107, 108)
+MESH_CHEEK_L = (117, 118, 101, 36, 205, 187, 123)
+MESH_CHEEK_R = (346, 347, 330, 266, 425, 411, 352)
+
+
+def ratio_polygons(bb, n_vertices: int = 36, parts=FACE_PARTS, shape: str = "ellipse"):
+    """(T,4) bounding boxes -> (polys int32 (T,K,V,2), nverts int32 (T,K)).  Part rectangles come
+    from ``roi_coords`` (the reference's float64 -> int() arithmetic); ``shape="ellipse"`` inscribes
+    an ellipse sampled at ``n_vertices`` angles (vertex = floor of the real point), ``shape="rect"``
+    gives the closed 4-gon (x1,y1) .. (x2-1,y2-1), whose mask is exactly the half-open rectangle."""
+    bb = np.asarray(bb, dtype=np.int64).reshape(-1, 4)
+    T = bb.shape[0]
+    V = 4 if shape == "rect" else int(n_vertices)
+    polys = np.zeros((T, len(parts), V, 2), dtype=np.int32)
+    ang = 2.0 * np.pi * np.arange(V, dtype=np.float64) / V
+    for k, (_, ratios, (lo, hi)) in enumerate(parts):
+        r = roi_coords(bb, *ratios).astype(np.float64)
+        x1 = r[:, 0] + lo * (r[:, 2] - r[:, 0])
+        x2 = r[:, 0] + hi * (r[:, 2] - r[:, 0])
+        y1, y2 = r[:, 1], r[:, 3]
+        if shape == "rect":
+            xa, xb, ya, yb = _trunc(x1), _trunc(x2) - 1, _trunc(y1), _trunc(y2) - 1
+            polys[:, k, :, 0] = np.stack([xa, xb, xb, xa], 1)
+            polys[:, k, :, 1] = np.stack([ya, ya, yb, yb], 1)
+        else:
+            cx, cy = 0.5 * (x1 + x2 - 1), 0.5 * (y1 + y2 - 1)
+            rx, ry = 0.5 * (x2 - 1 - x1), 0.5 * (y2 - 1 - y1)
+            polys[:, k, :, 0] = np.floor(cx[:, None] + np.maximum(rx, 0)[:, None] * np.cos(ang)[None] + 0.5)
+            polys[:, k, :, 1] = np.floor(cy[:, None] + np.maximum(ry, 0)[:, None] * np.sin(ang)[None] + 0.5)
+    return polys, np.full((T, len(parts)), V, dtype=np.int32)
+
+
+def landmark_polygons(landmarks, w: int, h: int, index_lists=(MESH_FOREHEAD, MESH_CHEEK_L, MESH_CHEEK_R)):
+    """Outlines through mesh landmarks: vertex = (int(x * w), int(y * h)), the truncation the
+    reference applies to landmark coordinates (rppg_VIDEO.py:95-98).  landmarks (T,N,2) ->
+    (polys int32 (T,K,Vmax,2), nverts int32 (T,K))."""
+    lm = np.asarray(landmarks, dtype=np.float64)
+    if lm.ndim == 2:
+        lm = lm[None]
+    T = lm.shape[0]
+    V = max(len(ix) for ix in index_lists)
+    polys = np.zeros((T, len(index_lists), V, 2), dtype=np.int32)
+    nverts = np.zeros((T, len(index_lists)), dtype=np.int32)
+    for k, ix in enumerate(index_lists):
+        ix = np.asarray(ix, dtype=np.int64)
+        polys[:, k, :len(ix), 0] = _trunc(lm[:, ix, 0] * w)
+        polys[:, k, :len(ix), 1] = _trunc(lm[:, ix, 1] * h)
+        nverts[:, k] = len(ix)
+    return polys, nverts
+
+
+def face_polygons(landmarks, w: int, h: int, n_vertices: int = 36):
+    """The forehead + two-cheek outlines of a landmark track: through the mesh landmarks when the
+    track has the FaceMesh topology (>= 468 points), otherwise ellipses in the reference's ratio
+    rectangles of the clamped landmark bounding box."""
+    lm = np.asarray(landmarks, dtype=np.float64)
+    if lm.ndim == 2:
+        lm = lm[None]
+    if lm.shape[1] >= 468:
+        return landmark_polygons(lm, w, h)
+    return ratio_polygons(bbox_clamped(lm, w, h), n_vertices)
+
+
 def slice_rects(rects, w: int, h: int):
     """Apply NumPy basic-slice semantics of ``frame[y1:y2, x1:x2]`` (rppg_VIDEO.py:106;
     roi.py:104) to (T,4) coordinates: negative indices wrap once, then clamp; reversed

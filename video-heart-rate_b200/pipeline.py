@@ -4,6 +4,8 @@
 ``video_bpm_series``    rppg_VIDEO.py:354-416 signal part (process_frame + sliding window)
 ``evm_bpm``             EVM (pyramid -> ideal bandpass -> collapse) + ROI mean + BPM, the
                         BASELINE.json configs c2/c4 (no reference code for the EVM part)
+``SlidingEvm``          rppg_LIVESTREAM.py-style sliding window (BASELINE.json config c3): frames
+                        arrive hop by hop from HOST memory, one BPM per hop
 """
 from __future__ import annotations
 
@@ -155,20 +157,80 @@ def video_bpm_series(eng: Engine, green, fps: float, band=VIDEO_BAND, window_sec
     return out
 
 
-def evm_bpm(eng: Engine, frames, fps: float, rects, levels: int = 4, band=EVM_BAND, alpha: float = 50.0,
+def evm_bpm(eng: Engine, frames, fps: float, rects=None, levels: int = 4, band=EVM_BAND, alpha: float = 50.0,
             channel: int = 1, window_len: int | None = None, hop: int | None = None, bpm_band=ANALYSIS_BAND,
-            out_f32=True, out_u8=False):
-    """EVM + ROI + BPM on device-resident frames.  ``rects`` (T,K,4) already sliced to the
-    frame.  The BPM comes from the green mean of ROI 0 of the MAGNIFIED frames through the
-    analysis estimator (float32 detrend + FFT peak, green_avg.py:42-44 / estimate_bpm.py) over
-    sliding windows (default: one window = the whole clip).
-    -> dict(roi_mean (T,K,3) device, bpm (n_win,), bin (n_win,), out_f32/out_u8)."""
+            out_f32=True, out_u8=False, polys=None, nverts=None):
+    """EVM + ROI + BPM on device-resident frames.  ROIs: ``rects`` (T,K,4) already sliced to the
+    frame, or landmark polygons ``polys`` (T,K,V,2) + ``nverts`` (T,K) (forehead / cheeks,
+    ``host.face_polygons``).  The BPM comes from the ``channel`` (green) means of the MAGNIFIED
+    frames through the analysis estimator (float32 detrend + FFT peak, green_avg.py:42-44 /
+    estimate_bpm.py) over sliding windows (default: one window = the whole clip): ROI 0 for
+    rectangles; for polygons all K ROI traces go in as the columns of a (T,K) signal and the
+    estimator keeps the column with the strongest in-band peak (estimate_bpm.py:59-64).
+    -> dict(roi_mean (T,K,3) device, roi_count, bpm (n_win,), bin (n_win,), out_f32/out_u8)."""
     fr = _frames_to_device(eng, frames)
     T = fr.shape[0]
-    r = eng.evm(fr, fps, levels, band[0], band[1], alpha, rects=rects, out_f32=out_f32, out_u8=out_u8)
-    green = r["roi_mean"][:, 0, channel].contiguous()
+    r = eng.evm(fr, fps, levels, band[0], band[1], alpha, rects=rects, out_f32=out_f32, out_u8=out_u8, polys=polys,
+                nverts=nverts)
+    # strided views: vhr_bpm_fft reads them through its row / column strides
+    green = r["roi_mean"][:, 0, channel] if polys is None else r["roi_mean"][:, :, channel]
     wl = T if window_len is None else window_len
     st, ln = host.sliding_windows(T, wl, wl if hop is None else hop)
     bpm, kbin = eng.bpm_fft(green, st, ln, fps, bpm_band, detrend=DETREND_F32, mode=FFT_ANALYSIS)
     r.update({"bpm": bpm, "bin": kbin, "win_start": st, "win_len": ln})
     return r
+
+
+class SlidingEvm:
+    """Sliding-window EVM + ROI + BPM for a live stream (BASELINE.json config c3: 10 s window,
+    1 s hop; the reference's live loop is rppg_LIVESTREAM.py:311-349, which re-estimates on its
+    whole deque every frame).  ``push(frames_host, rects)`` takes the hop's new uint8 frames from
+    HOST memory (pinned for an asynchronous copy) and returns the window's BPM once the window is
+    full.  Per hop only the NEW frames are uploaded and reduced by the pyrDown cascade (a frame's
+    pyramid does not depend on its neighbours); the level-L window and the frame window slide on
+    the device (two buffers, device-to-device copies); the temporal bandpass and the ROI-only
+    collapse run on the whole window.  Every number equals ``evm_bpm`` on the same window, bit for
+    bit (same kernels on the same per-frame data)."""
+
+    def __init__(self, eng: Engine, H: int, W: int, fps: float, window_len: int, hop: int, K: int = 1, levels: int = 4,
+                 band=EVM_BAND, alpha: float = 50.0, bpm_band=ANALYSIS_BAND, channel: int = 1):
+        import torch
+        self.eng, self.fps, self.n, self.hop, self.levels = eng, float(fps), int(window_len), int(hop), levels
+        self.band, self.alpha, self.bpm_band, self.channel = band, alpha, bpm_band, channel
+        wl, hl = eng.pyr_dims(W, H, levels)[-1]
+        d = eng.tdev
+        self.frames = [torch.empty((self.n, H, W, 3), dtype=torch.uint8, device=d) for _ in range(2)]
+        self.level = [torch.empty((self.n, hl, wl, 3), dtype=torch.float32, device=d) for _ in range(2)]
+        self.rects = [torch.zeros((self.n, K, 4), dtype=torch.int32, device=d) for _ in range(2)]
+        self.filt = torch.empty((self.n, hl, wl, 3), dtype=torch.float32, device=d)
+        self.cur, self.have = 0, 0
+        self.st = torch.zeros(1, dtype=torch.int32, device=d)
+        self.ln = torch.full((1,), self.n, dtype=torch.int32, device=d)
+
+    def push(self, frames_host, rects):
+        """frames_host uint8 (m,H,W,3) host tensor / array (m <= window), rects int32 (m,K,4).
+        -> (bpm float, bin int) of the window ending with these frames, or None while filling."""
+        import torch
+        fh = frames_host if isinstance(frames_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(frames_host))
+        rh = torch.as_tensor(np.ascontiguousarray(rects, dtype=np.int32)).reshape(fh.shape[0], -1, 4)
+        m = int(fh.shape[0])
+        src, dst = self.cur, 1 - self.cur
+        keep = min(self.have, self.n - m)
+        if keep > 0:            # slide: the newest `keep` frames of the old window move to the front of the other buffer
+            a = self.have - keep
+            self.frames[dst][:keep].copy_(self.frames[src][a:a + keep], non_blocking=True)
+            self.level[dst][:keep].copy_(self.level[src][a:a + keep], non_blocking=True)
+            self.rects[dst][:keep].copy_(self.rects[src][a:a + keep], non_blocking=True)
+        self.frames[dst][keep:keep + m].copy_(fh, non_blocking=True)                      # H2D of the hop
+        self.rects[dst][keep:keep + m].copy_(rh, non_blocking=True)
+        self.eng.pyrdown(self.frames[dst][keep:keep + m], self.levels, out=self.level[dst][keep:keep + m])
+        self.cur, self.have = dst, keep + m
+        if self.have < self.n:
+            return None
+        e = self.eng
+        e.bandpass(self.level[dst], self.fps, self.band[0], self.band[1], self.alpha, out=self.filt)
+        _, _, means = e.collapse(self.filt, self.frames[dst], self.levels, out_f32=False, out_u8=False, rects=self.rects[dst])
+        bpm, kbin = e.bpm_fft(means[:, 0, self.channel], self.st, self.ln, self.fps, self.bpm_band, detrend=DETREND_F32,
+                              mode=FFT_ANALYSIS, max_len=self.n)
+        self.last_means = means
+        return float(bpm[0].item()), int(kbin[0].item())                                   # D2H of the result
