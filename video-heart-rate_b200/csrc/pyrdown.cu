@@ -26,6 +26,8 @@
 // fast path for W % 16 == 0 (pyrdown_fast.cu); VHR_ERR_UNSUPPORTED when the shape is not eligible
 int vhr_pyrdown_fast(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int W, int levels, float* d_level,
                      cudaStream_t stream);
+int vhr_pyrdown_mma(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int W, int levels, float* d_level,
+                    cudaStream_t stream);
 int vhr_pyrdown_stream(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int W, int levels, float* d_level,
                        cudaStream_t stream);
 
@@ -344,12 +346,14 @@ extern "C" int vhr_pyrdown_cascade(vhr_ctx* ctx, const uint8_t* d_frames, int T,
     VHR_REQUIRE(ctx, levels >= 1 && levels <= VHR_MAX_LEVELS, "levels must be 1..6");
     VHR_REQUIRE(ctx, W <= 8192, "W > 8192 unsupported");
     {
-        // test hooks: VHR_PYRDOWN_GENERIC=1 forces the generic kernel, VHR_PYRDOWN_IMPL=fast skips the streaming kernel
+        // test hooks: VHR_PYRDOWN_GENERIC=1 forces the generic kernel; VHR_PYRDOWN_IMPL=stream skips the tensor-core
+        // streaming kernel (pyrdown_mma.cu), =fast skips both streaming kernels
         const char* force = getenv("VHR_PYRDOWN_GENERIC");
         const char* impl = getenv("VHR_PYRDOWN_IMPL");
         if (!(force && force[0] == '1')) {
             int rc = VHR_ERR_UNSUPPORTED;
-            if (!(impl && impl[0] == 'f')) rc = vhr_pyrdown_stream(ctx, d_frames, T, H, W, levels, d_level, (cudaStream_t)stream);
+            if (!(impl && (impl[0] == 'f' || impl[0] == 's'))) rc = vhr_pyrdown_mma(ctx, d_frames, T, H, W, levels, d_level, (cudaStream_t)stream);
+            if (rc == VHR_ERR_UNSUPPORTED && !(impl && impl[0] == 'f')) rc = vhr_pyrdown_stream(ctx, d_frames, T, H, W, levels, d_level, (cudaStream_t)stream);
             if (rc == VHR_ERR_UNSUPPORTED) rc = vhr_pyrdown_fast(ctx, d_frames, T, H, W, levels, d_level, (cudaStream_t)stream);
             if (rc != VHR_ERR_UNSUPPORTED) return rc;
         }
