@@ -189,6 +189,20 @@ int vhr_bpm_welch(vhr_ctx* ctx, const double* d_trace, int n_trace,
 int vhr_sos_causal(vhr_ctx* ctx, const double* d_x, int n, const double* h_sos, int n_sec,
                    double* d_state, double* d_y, void* stream);
 
+/* ---- ICA measurement: analysis/measurement/ica.py:36-72 ----------------------------
+ * Batched FastICA (3 components, parallel algorithm, logcosh, unit-variance whitening; scikit-learn's
+ * algorithm, which the reference calls at ica.py:36-44,65) over windows of a mean-BGR trace:
+ * d_trace float64 (n_trace,3); window w = rows [start[w], start[w]+len[w]).  Per window: float32 cast and
+ * per-channel std normalisation (ddof = 1, ica.py:56-61), centring, whitening, fixed point from the 3x3
+ * start matrix h_w_init (row-major; the reference's is RandomState(0).normal(size=(3,3))), at most max_iter
+ * iterations, tolerance tol.  d_sources float64 (n_win, max_len, 3) gets the unit-variance sources (NaN
+ * padding behind len[w]); d_n_iter int32 (n_win) the iterations used, NEGATED when the fixed point did not
+ * reach tol (the reference skips such windows, ica.py:64-69).  Feed d_sources to vhr_bpm_fft with C = 3
+ * (ica.py:72).  Float64 arithmetic: tolerance contract, not bit parity (see csrc/ica.cu). */
+int vhr_ica_fastica(vhr_ctx* ctx, const double* d_trace, int n_trace, const int32_t* d_start,
+                    const int32_t* d_len, int n_win, int max_len, const double* h_w_init,
+                    int max_iter, double tol, double* d_sources, int32_t* d_n_iter, void* stream);
+
 /* ---- analysis-harness degradations and metric ---------------------------
  * Additive noise: clip(float(frame) + noise, 0, 255) truncated to uint8 -- analysis/degradation/
  * colour_noise.py:11-24.  The reference draws np.random.normal; here the draw is a counter-based

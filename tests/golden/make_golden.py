@@ -249,6 +249,34 @@ def gen_bpm_extra(out):
     print("bpm_extra:", i, "psd windows,", j, "multi-column signals,", k, "signed-band cases")
 
 
+def gen_ica(out):
+    """analysis/measurement/ica.py:24-76 replayed on synthetic mean-BGR traces (ica.npz): the loop of
+    oracle.ica.ica_series with the reference's own ``estimate_bpm`` (executed verbatim) and scikit-learn's FastICA
+    with the reference's arguments.  Per analysed frame: converged flag, BPM."""
+    import types
+    from oracle import ica as oica
+    A = ref_loader.load_functions("analysis/utils/estimate_bpm.py", ["estimate_bpm"], extra_ns={"plt": types.SimpleNamespace()})
+    rng = np.random.default_rng(1357)
+    rec = {}
+    cases = [(30.0, 420, 1.3, 0.6), (30.0, 360, 1.9, 0.25), (10.0, 200, 1.1, 0.4), (25.0, 300, 2.4, 1.0)]
+    for j, (fps, T, f_hz, noise) in enumerate(cases):
+        t = np.arange(T) / fps
+        pulse = np.sin(2 * np.pi * f_hz * t + rng.uniform(0, 6.28))
+        mix = rng.uniform(0.3, 1.0, 3)
+        bgr = np.stack([110 + 20 * c + mix[c] * pulse + noise * rng.standard_normal(T) + 0.4 * np.sin(2 * np.pi * 0.25 * t + c)
+                        for c in range(3)], 1)
+        res = oica.ica_series(bgr, fps, estimate=lambda s, fs: A["estimate_bpm"](s, fs=fs))
+        rec[f"ica_bgr_{j}"] = bgr
+        rec[f"ica_fps_{j}"] = np.float64(fps)
+        rec[f"ica_frame_{j}"] = np.array([r[0] for r in res], dtype=np.int32)
+        rec[f"ica_conv_{j}"] = np.array([r[1] for r in res], dtype=bool)
+        rec[f"ica_bpm_{j}"] = np.array([np.nan if r[2] is None else r[2] for r in res], dtype=np.float64)
+    rec["n_ica"] = len(cases)
+    np.savez_compressed(os.path.join(out, "ica.npz"), **rec)
+    print("ica:", len(cases), "traces,", sum(len(rec[f"ica_frame_{j}"]) for j in range(len(cases))), "windows,",
+          sum(int(rec[f"ica_conv_{j}"].sum()) for j in range(len(cases))), "converged in scikit-learn")
+
+
 def main():
     if not ref_loader.available():
         raise SystemExit("reference tree not found; golden vectors can only be made in the build container")
@@ -256,6 +284,7 @@ def main():
     gen_bpm(HERE)
     gen_metrics(HERE)
     gen_bpm_extra(HERE)
+    gen_ica(HERE)
 
 
 if __name__ == "__main__":

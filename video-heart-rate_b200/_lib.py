@@ -48,6 +48,8 @@ SIGNATURES = {
                               c_int, c_int, c_void_p, c_int, c_double, c_void_p, c_void_p, c_void_p, c_int,
                               c_void_p]),
     "vhr_sos_causal": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "vhr_ica_fastica": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_double,
+                                c_void_p, c_void_p, c_void_p]),
     "vhr_degrade_noise_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, C.c_uint32, C.c_uint32,
                                      c_int, c_void_p]),
     "vhr_degrade_quantise_u8": (c_int, [c_void_p, c_void_p, c_void_p, C.c_longlong, c_int, c_void_p]),

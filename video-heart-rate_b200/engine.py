@@ -329,6 +329,30 @@ class Engine:
                                            self._stream()), "vhr_bpm_welch")
         return bpm, kbin, filt
 
+    def ica_fastica(self, trace, starts, lens, w_init: Optional[np.ndarray] = None, max_iter: int = 300, tol: float = 1e-6):
+        """Batched FastICA over windows of a mean-BGR trace (analysis/measurement/ica.py:36-69): trace float64
+        (n,3), windows (start,len) -> (sources float64 (n_win, max_len, 3) device, n_iter int32 (n_win) device;
+        negative where the fixed point did not reach ``tol`` -- the reference skips those windows).  ``w_init``
+        defaults to the reference's ``FastICA(random_state=0)`` start matrix."""
+        torch = _torch()
+        tr = self._dev(trace, torch.float64).reshape(-1, 3)
+        n = tr.shape[0]
+        lens_np = np.asarray(lens if not isinstance(lens, torch.Tensor) else lens.cpu(), dtype=np.int64)
+        st, ln = self._dev(starts, torch.int32), self._dev(lens, torch.int32)
+        nw = st.numel()
+        max_len = int(min(n, max(1, lens_np.max()))) if nw else 1
+        src = torch.empty((nw, max_len, 3), dtype=torch.float64, device=self.tdev)
+        nit = torch.empty(nw, dtype=torch.int32, device=self.tdev)
+        if nw == 0:
+            return src, nit
+        if w_init is None:
+            w_init = np.random.RandomState(0).normal(size=(3, 3))       # check_random_state(0) at every fit (ica.py:43)
+        w = np.ascontiguousarray(w_init, dtype=np.float64).reshape(3, 3)
+        self._check(self.lib.vhr_ica_fastica(self.ctx, self._p(tr), n, self._p(st), self._p(ln), nw, max_len,
+                                             C.c_void_p(w.ctypes.data), int(max_iter), float(tol), self._p(src), self._p(nit),
+                                             self._stream()), "vhr_ica_fastica")
+        return src, nit
+
     def sos_causal(self, x, sos: np.ndarray, state):
         """Causal SOS filter with carried state (n_sec,2) float64 device tensor (updated)."""
         torch = _torch()

@@ -70,6 +70,37 @@ def green_avg_measure(eng: Engine, frames, fps: float, landmarks, valid=None, ch
     return np.column_stack([ts[ok], bpm[ok]])
 
 
+def ica_measure(eng: Engine, frames, fps: float, landmarks, valid=None, window_s: float = 10.0, acq_s: float = 5.0,
+                band=ANALYSIS_BAND, max_iter: int = 300, tol: float = 1e-6, return_details: bool = False):
+    """analysis/measurement/ica.py:measure on decoded frames + landmarks -> (M,2) float64 [t_sec, bpm]:
+    per-frame mean BGR of the cheek ROI (:48), growing 5 s -> 10 s window (:27-29, :52), float32 cast + ddof=1
+    std normalisation (:56-61), FastICA (3 components, parallel, logcosh, tol 1e-6, 300 iterations, seed 0;
+    :36-44) on the device, windows whose fixed point does not converge are skipped (:64-69), BPM = FFT peak
+    of the source with the strongest in-band peak (:72, estimate_bpm.py:59-64)."""
+    import torch
+    means, usable = green_avg_trace(eng, frames, landmarks, valid)          # (T,3) in the frames' channel order (BGR from cv2)
+    idx_all = np.arange(means.shape[0])
+    if not usable.all():
+        keep = torch.as_tensor(np.nonzero(usable)[0], device=eng.tdev)
+        means = means[keep]
+        idx_all = idx_all[usable]
+    means = means.contiguous()
+    n = int(means.shape[0])
+    fi, st, ln = host.green_avg_windows(n, fps, window_s, acq_s)
+    if len(fi) == 0:
+        return (np.zeros((0, 2)), None) if return_details else np.zeros((0, 2))
+    src, nit = eng.ica_fastica(means, st, ln, max_iter=max_iter, tol=tol)
+    nw, ml, _ = src.shape
+    starts2 = (np.arange(nw, dtype=np.int64) * ml).astype(np.int32)
+    bpm, kbin = eng.bpm_fft(src.reshape(nw * ml, 3), starts2, ln, fps, band, detrend=DETREND_NONE, mode=FFT_ANALYSIS, max_len=ml)
+    bpm, nit_h = bpm.cpu().numpy(), nit.cpu().numpy()
+    ok = (nit_h > 0) & ~np.isnan(bpm)
+    rows = np.column_stack([(idx_all[fi] * (1 / fps))[ok], bpm[ok]])
+    if return_details:
+        return rows, {"frame": idx_all[fi], "bpm": bpm, "bin": kbin.cpu().numpy(), "n_iter": nit_h}
+    return rows
+
+
 def green_avg_psd_series(eng: Engine, green, fps: float, band=ANALYSIS_BAND, window_s: float = 10.0, acq_s: float = 10.0,
                          order: int = 2) -> np.ndarray:
     """The BPM series of analysis/measurement/green_avg_psd_plot.py:160-185 given the per-frame green
