@@ -72,7 +72,7 @@ def test_pyrdown_cascade(vhr, eng, hw, levels):
 
 
 def test_pyrdown_generic_kernel_on_aligned_shapes(vhr, eng, monkeypatch):
-    """The generic kernel (used for W % 16 != 0) gives the same bits as the fast path."""
+    """The generic kernel (used for W % 16 != 0) gives the same values as the streaming kernel."""
     import torch
     monkeypatch.setenv("VHR_PYRDOWN_GENERIC", "1")
     rng = np.random.default_rng(77)
@@ -98,33 +98,37 @@ def test_pyrdown_many_frames_persistent_split(vhr, eng):
 
 
 @pytest.mark.parametrize("case", [(400, 70, 128, 4), (300, 70, 128, 3), (2, 40, 3840, 4), (2, 33, 2048, 3),
-                                  (3, 200, 256, 5), (2, 130, 320, 6), (5, 1080, 1920, 4), (40, 36, 64, 2)])
-def test_pyrdown_stream_kernel(vhr, eng, case, monkeypatch):
-    """The streaming kernel (W % 64 == 0: registers + shuffles for levels 1-2, per-warp TMA input rings,
-    upper levels by one warp in turn) on shapes that exercise shares crossing frames, the 512-thread
-    variant (W > 1920), 5 and 6 levels, odd level heights; held to the oracle and to the previous fast
-    path (same arithmetic, block barriers)."""
+                                  (3, 200, 256, 5), (2, 130, 320, 6), (5, 1080, 1920, 4), (40, 36, 64, 2),
+                                  (3, 90, 720, 4), (6, 61, 1296, 3), (2, 48, 3072, 4), (30, 40, 96, 5), (4, 135, 240, 1)])
+def test_pyrdown_streaming_kernels(vhr, eng, case, monkeypatch):
+    """The two streaming kernels on shapes that exercise shares crossing frames, wide frames, 5 and 6 levels, odd level
+    heights, widths only one of them takes (W % 64 != 0: tensor-core kernel only; 6 levels or W % 2^L != 0: streaming
+    kernel only): pyrdown_stream.cu (registers + shuffles for levels 1-2, per-warp TMA input rings, upper levels by one
+    warp in turn) and pyrdown_mma.cu (banded 5-tap on IMMA tiles, one private pipeline per warp).  Each is held to the
+    oracle; where both apply they agree bit for bit on levels 1-2 and to 1e-6 above."""
     import torch
     T, H, W, levels = case
     rng = np.random.default_rng(T + H + W + levels)
     fr = rng.integers(0, 256, (T, H, W, 3), dtype=np.uint8)
     frd = torch.as_tensor(fr, device=eng.tdev)
-    got = eng.pyrdown(frd, levels).cpu().numpy()
     n_ref = min(T, 6)                                         # the oracle on the first and last frames
     sel = np.r_[0:n_ref // 2, T - (n_ref - n_ref // 2):T]
     ref = oevm.pyrdown_cascade(fr[sel], levels)
-    assert got.shape[1:] == ref.shape[1:]
+    outs = {}
+    for impl in ("stream", "mma"):
+        monkeypatch.setenv("VHR_PYRDOWN_IMPL", impl)
+        got = eng.pyrdown(frd, levels).cpu().numpy()
+        monkeypatch.delenv("VHR_PYRDOWN_IMPL")
+        assert got.shape[1:] == ref.shape[1:]
+        if levels <= 2:
+            np.testing.assert_array_equal(got[sel], ref.astype(np.float32))
+        else:
+            assert rel_err(got[sel], ref) <= REL
+        outs[impl] = got
     if levels <= 2:
-        np.testing.assert_array_equal(got[sel], ref.astype(np.float32))
+        np.testing.assert_array_equal(outs["stream"], outs["mma"])
     else:
-        assert rel_err(got[sel], ref) <= REL
-    monkeypatch.setenv("VHR_PYRDOWN_IMPL", "fast")
-    fast = eng.pyrdown(frd, levels).cpu().numpy()
-    monkeypatch.delenv("VHR_PYRDOWN_IMPL")
-    if levels <= 2:
-        np.testing.assert_array_equal(got, fast)
-    else:
-        assert rel_err(got, fast) <= 1e-6                     # every frame, every share boundary
+        assert rel_err(outs["stream"], outs["mma"]) <= 1e-6   # every frame, every share boundary
 
 
 # --------------------------------------------------------------------------------- bandpass

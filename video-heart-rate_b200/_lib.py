@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libvhr_b200.so")
+# VHR_LIB selects another build of the same library (the -DVHR_WATCHDOG one, csrc/build.py --watchdog)
+LIB_PATH = os.environ.get("VHR_LIB") or os.path.join(HERE, "csrc", "libvhr_b200.so")
 
 c_void_p, c_int, c_int64, c_double, c_float = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_float
 

@@ -1,6 +1,10 @@
 """Build libvhr_b200.so in-tree with nvcc for sm_100a (the only target).
 
-    python video-heart-rate_b200/csrc/build.py [--force] [--verbose]
+    python video-heart-rate_b200/csrc/build.py [--force] [--verbose] [--watchdog]
+
+--watchdog builds a second library, libvhr_b200_wd.so, with -DVHR_WATCHDOG: every hand-rolled mbarrier spin loop
+traps with a message after 2 M polls instead of hanging the GPU.  Select it with VHR_LIB=<path> (see _lib.py); the
+GPU suite is run against it once per round (profiles/).
 
 The .so is git-ignored but travels to the GPU box with the repo snapshot.
 """
@@ -11,7 +15,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["api.cu", "synth.cu", "pyrdown.cu", "pyrdown_fast.cu", "pyrdown_stream.cu", "pyrdown_mma.cu", "bandpass.cu", "collapse_sep.cu", "roi.cu", "bpm.cu", "ica.cu", "degrade.cu", "hostpath.cu"]
+SOURCES = ["api.cu", "synth.cu", "pyrdown.cu", "pyrdown_stream.cu", "pyrdown_mma.cu", "bandpass.cu", "collapse_sep.cu", "roi.cu", "bpm.cu", "ica.cu", "degrade.cu", "hostpath.cu"]
 LIB = os.path.join(HERE, "libvhr_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
@@ -33,15 +37,16 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, watchdog: bool = False) -> str:
+    lib = LIB.replace(".so", "_wd.so") if watchdog else LIB
+    if not force and not watchdog and not needs_build():
         return LIB
     nvcc = _nvcc()
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + (["-DVHR_WATCHDOG"] if watchdog else [])
     objs = []
     procs = []
     for s in SOURCES:
-        o = os.path.join(HERE, s.replace(".cu", ".o"))
+        o = os.path.join(HERE, s.replace(".cu", "_wd.o" if watchdog else ".o"))
         objs.append(o)
         cmd = [nvcc, *flags, "-c", os.path.join(HERE, s), "-o", o]
         if verbose:
@@ -57,10 +62,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("nvcc compilation failed")
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
+    cmd = [nvcc, "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
     subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, watchdog="--watchdog" in sys.argv))

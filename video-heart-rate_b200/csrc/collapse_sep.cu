@@ -80,6 +80,20 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
 }
+#ifdef VHR_WATCHDOG
+__device__ __noinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    for (long long spin = 0;; ++spin) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+        if (spin > 2000000) {
+            if ((threadIdx.x & 31) == 0) printf("WATCHDOG(collapse) block %d warp %d parity %u\n", blockIdx.x, threadIdx.x >> 5, parity);
+            __trap();
+        }
+    }
+}
+#else
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n"
@@ -88,6 +102,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "@!p bra W_%=;\n\t}"
         :: "r"(bar), "r"(parity) : "memory");
 }
+#endif
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");

@@ -1,31 +1,35 @@
-// Streaming pyrDown cascade, integer-tensor-core form (W % 16 == 0; W % 64 == 0 for >= 3 levels; 16-byte
-// aligned frames).  Same spec as pyrdown.cu (cv2.pyrDown float32 semantics; levels 1-2 exact integers * 2^-8l),
-// same streaming skeleton as pyrdown_stream.cu (persistent grid over (frame, final-row) shares, one private
-// TMA input ring per warp, levels >= 3 by one warp per level-2 row in turn) -- what changes is where the
-// instructions of levels 1 and 2 go.  The ncu captures of the previous kernel (profiles/r1_ncu_p_*) showed it
-// issue-bound at 39 % of DRAM peak: ~220 instructions per level-1 row and warp, two thirds of them byte
-// unpacking (PRMT), dot products (IDP2A) and shuffles of the HORIZONTAL 5-tap passes.  Here
+// Streaming pyrDown cascade, integer-tensor-core form, ONE WARP = ONE PRIVATE PIPELINE (W % 16 == 0 and
+// W % 2^levels == 0, levels <= 5, 16-byte aligned frames; other shapes take pyrdown_stream.cu / pyrdown.cu).
+// Same spec as pyrdown.cu (cv2.pyrDown float32 semantics; levels 1-2 exact integers * 2^-8l).
 //
-//   * the horizontal 5-tap, stride-2, 3-channel-interleaved filter is a banded matrix, evaluated on the raw
-//     uint8 row bytes by mma.sync.m16n8k32 (u8 x u8 -> s32, SASS IMMA.16832): one MMA column = one block
-//     of 16 consecutive output values (interleaved channel bytes), whose 45-byte input window sits inside
-//     K = 64 = two k-steps; the 8 columns of an MMA are blocks 3 apart, so that all of them have the same
-//     channel phase and share one constant weight fragment (three phases, 24 registers of constants built
-//     once per thread).  A lane feeds the MMA with plain 8-byte shared-memory loads of the row (the K order
-//     of the fragment is permuted to make them contiguous) -- no unpacking, no shuffles, exact s32 sums;
-//   * the vertical pass runs on the accumulators, packed two 16-bit values per register (<= 65280), in the
-//     incremental form out = A + 4 n1 + n2, A' = C + 4 n1 + 6 n2, C' = n2 of the previous kernel;
-//   * a finished level-1 row (16-bit values) is split into a low-byte and a high-byte plane in a private
-//     shared-memory strip and goes through the SAME banded MMA twice (the weights are the same: level 1 is
-//     3-channel interleaved too); lo + 256 hi recombine exactly in s32; level-2 vertical pass incremental
-//     with three s32 partial sums per value (A, B = 4 r(2q-1) + r(2q-2) for the bottom border, C);
-//   * a warp owns 60 level-2 pixels and RECOMPUTES the 8 level-1 values either side that its level-2 window
-//     needs (384 level-1 values computed for 360 owned), so warps still never exchange level-1 data;
-//   * frame borders (reflect-101 on the left / right) are patched into the shared-memory rows (6 + 3 bytes
-//     per row, edge warps only) instead of being special-cased in the arithmetic.
-//
-// Level 2 rows go to the shared level-2 ring (interleaved RGB floats now) and levels >= 3 proceed exactly as
-// in pyrdown_stream.cu.  Bit-exactness of levels 1-2 is unchanged (integer arithmetic throughout).
+// What the ncu captures of the previous kernels said (profiles/README.md, round 2):
+//   * pyrdown_stream.cu is issue-bound in its main loop (~220 instructions per level-1 row and warp, two thirds
+//     of them byte unpacking, IDP2A dot products and shuffles of the HORIZONTAL 5-tap passes), and
+//   * behind that, BOTH it and the first tensor-core cut were bound by the serial upper-level chain: levels >= 3
+//     of a level-2 row were run by one warp, each row waiting for the previous one (~4 300 - 7 000 cycles per
+//     row and CTA whatever the main loop cost; a third of the stall samples sat in mbarrier spins).
+// Hence this design:
+//   * horizontal passes of levels 1 and 2 on the integer tensor cores: the 5-tap, stride-2, 3-channel-interleaved
+//     filter is a banded matrix, evaluated on the raw uint8 row bytes by mma.sync.m16n8k32 (u8 x u8 -> s32, SASS
+//     IMMA.16832).  One MMA column = one block of 16 consecutive output values (interleaved channel bytes), whose
+//     45-byte input window sits inside K = 64 = two k-steps; the 8 columns of an MMA are blocks 3 apart, so that
+//     all of them have the same channel phase and share one constant weight fragment (three phases, 24 registers
+//     of constants built once per thread).  A lane feeds the MMA with plain 8-byte shared-memory loads of the row
+//     (the K order of the fragment is permuted to make them contiguous): no unpacking, no shuffles, exact sums;
+//   * vertical passes on the accumulators: level 1 packed two 16-bit values per register (<= 65280) in the
+//     incremental form out = A + 4 n1 + n2, A' = C + 4 n1 + 6 n2, C' = n2; a finished level-1 row is split into a
+//     low-byte and a high-byte plane in a private shared-memory strip and goes through the SAME banded MMA twice
+//     (level 1 is 3-channel interleaved too; lo + 256 hi recombine exactly in s32); level-2 vertical pass
+//     incremental with two s32 partial sums per value;
+//   * NO cross-warp communication at all.  A warp owns a strip of the FINAL level (12 px of level 4 at 4 levels)
+//     and computes, privately, everything that strip depends on: 60 px of level 2 (for 48 owned), 128 px of level 1,
+//     a 832-byte window of every input row that it fetches itself (TMA tensor box into its own ring).  Levels >= 3
+//     run inline in the same warp, one lane per pixel, from small per-warp strips / 5-row H rings.  The price is
+//     25 % redundant work at the strip borders; what it buys: no barrier wider than a warp, no spin loop except
+//     the wait for the warp's own input rows, no serial chain.  A CTA is only a container of such warps;
+//   * frame borders (reflect-101 left / right) are patched into the shared-memory rows of each level (6 + 3
+//     values per row, edge strips only) instead of being special-cased in the arithmetic.
+// Levels 1-2 stay bit-exact (integer arithmetic throughout); levels >= 3 are float32 as before.
 #include "common.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -33,13 +37,14 @@
 namespace {
 
 constexpr int HR = 5;        // rows in a private H ring (exactly the vertical footprint)
-constexpr int LANES = 30;    // 8-pixel input column groups owned by a warp (= 240 input px = 120 px of level 1 = 60 px of level 2)
-constexpr int WSLOT = 832;   // bytes of one input row in a warp's ring: ring byte b <-> input byte 720 w - 32 + b
+constexpr int WSLOT = 832;   // bytes of one input row in a warp's ring (24 blocks x 32 bytes + the 64-byte window of the last one)
 constexpr int GBYTES = 2 * WSLOT;   // input rows travel in groups of two = one TMA box, a multiple of 128 bytes
-constexpr int RS = 4;        // level-2 ring slots = rows a warp may run ahead of the upper levels
-constexpr int DLY = 2;       // the upper levels of row n start when their warp has published row n + DLY
 constexpr int PLANE = 512;   // bytes of one byte plane (low / high) of a warp's level-1 row: 384 values + over-read room
-constexpr int OWN2 = 6 * LANES;   // level-2 values (interleaved channel bytes) owned by a warp: 60 px x 3
+constexpr int N2 = 60;       // level-2 pixels a warp computes (12 MMA blocks of 16 values; the last 12 values are not valid)
+constexpr int MAXL = 5;      // deepest pyramid this kernel takes (the strip a warp can own shrinks as 60 -> 24 -> 12 -> 4 px)
+
+// pixels of level l (>= 2) a warp computes: 60, 28, 12, 4
+__host__ __device__ constexpr int ncomp(int l) { return l == 2 ? 60 : l == 3 ? 28 : l == 4 ? 12 : 4; }
 
 struct MmaArgs {
     const uint8_t* frames;
@@ -48,16 +53,16 @@ struct MmaArgs {
     int w[VHR_MAX_LEVELS + 1];
     int h[VHR_MAX_LEVELS + 1];
     long long total_rows;
-    int nt;                                // column groups = W / 8
-    int ng;                                // two-row groups in each warp's input ring
-    int rowbytes;                          // 3 W
-    int in_off;                            // byte offset of warp 0's input ring (warp w: + w * ng * GBYTES), 128-B aligned
-    int plane_off;                         // byte offset of warp 0's level-1 planes (warp w: + w * 2 * PLANE)
-    int rbar_off;                          // byte offset of the RS row barriers, followed by the RS duty barriers
-    int ring_off[VHR_MAX_LEVELS + 1];      // level 2: RS rows, interleaved (px + 2) * 3 + ch; levels 3..L-1: planar, double-buffered
-    int ring_stride[VHR_MAX_LEVELS + 1];   // floats per row (level 2) / per channel plane row (levels >= 3)
-    int hring_off[VHR_MAX_LEVELS + 1];     // levels 3..L: H rings (HR rows x 3 planes x w[l])
-    int duty_off;                          // DutyState
+    int ng;                   // two-row groups in each warp's input ring
+    int rowbytes;             // 3 W
+    int strips, wpc, ncg;     // strips per row, warps (strips) per CTA, CTAs per row share (column groups)
+    int own;                  // pixels of the final level a strip owns (level-1 pixels when levels == 1)
+    int step[MAXL + 1];       // first computed pixel of level l (2..L) in strip s: step[l] * s + boff[l]
+    int boff[MAXL + 1];
+    int warp_smem;            // bytes of shared memory per warp: [ng mbarriers][input ring][planes][strips / H rings]
+    int in_off, plane_off;    // offsets inside a warp's block
+    int strip_off[MAXL + 1];  // level l (2..L-1): finished row, interleaved floats (3 per pixel)
+    int hring_off[MAXL + 1];  // level l (3..L): HR rows of horizontal sums
 };
 
 // ---- PTX helpers ---------------------------------------------------------------------------
@@ -97,33 +102,18 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-// D += A(16x32, u8, row) * B(32x8, u8, col); s32 accumulators (SASS: IMMA.16832.U8.U8)
+// D = A(16x32, u8, row) * B(32x8, u8, col) [+ D]; s32 accumulators (SASS: IMMA.16832.U8.U8).  The first k-step of a
+// chain takes a zero C operand (RZ) instead of zero-filled accumulator registers.
+__device__ __forceinline__ void imma0(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+        : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "r"(0));
+}
 __device__ __forceinline__ void imma(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+        : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-
-// vector loads / stores of C consecutive floats (C = 4, 2, 1), naturally aligned
-template <int C>
-__device__ __forceinline__ void ldv(const float* p, float* x) {
-    if constexpr (C == 4) { const float4 v = *reinterpret_cast<const float4*>(p); x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w; }
-    else if constexpr (C == 2) { const float2 v = *reinterpret_cast<const float2*>(p); x[0] = v.x; x[1] = v.y; }
-    else x[0] = *p;
-}
-template <int C>
-__device__ __forceinline__ void stv(float* p, const float* x) {
-    if constexpr (C == 4) *reinterpret_cast<float4*>(p) = make_float4(x[0], x[1], x[2], x[3]);
-    else if constexpr (C == 2) *reinterpret_cast<float2*>(p) = make_float2(x[0], x[1]);
-    else *p = x[0];
-}
-
-// Block-shared state of the levels >= 3 (they are processed by one warp at a time, in turn).
-struct DutyState {
-    int nextr[VHR_MAX_LEVELS + 1];
-    int lastr[VHR_MAX_LEVELS + 1];
-    int hslot[VHR_MAX_LEVELS + 1];
-};
 
 // One register of the constant weight fragment (operand A of the MMA) of channel phase `phase`, k-step `ks`.
 // Row m of the fragment produces output value jl = 2 m (m < 8) or 2 (m - 8) + 1 of a 16-value block, so that a
@@ -153,22 +143,32 @@ __device__ __forceinline__ uint32_t weight_reg(int phase, int ks, int r, int lan
     return v;
 }
 
+// reflect-101 patch of one row held in shared memory (bytes or floats, 3 interleaved channels): idx0 = index of
+// pixel 0 / channel 0, idxe = index of pixel w (the first one right of the row); pixels -2, -1 <- 2, 1 and w <- w - 2.
+// Lanes 0..5 / 8..10 do the copies; the caller orders them with __syncwarp.
+template <typename Tv>
+__device__ __forceinline__ void patch_row(Tv* row, int idx0, bool left, int idxe, bool right, int lane) {
+    if (left && lane < 6) row[idx0 + lane - 6] = row[idx0 + (lane < 3 ? lane + 6 : lane)];
+    if (right && lane >= 8 && lane < 11) row[idxe + lane - 8] = row[idxe - 6 + lane - 8];
+}
+
 template <int L>
-struct Stream {
+struct Pipe {
     const MmaArgs& a;
     const CUtensorMap* tmap;
-    unsigned char* smem;
-    const int warp, lane;
+    unsigned char* wsm;       // this warp's shared-memory block
+    const int lane, strip;
     uint32_t AF[3][2][4];     // weight fragments: [channel phase][k-step][register]
     const unsigned char* rd;  // this lane's first operand bytes in row 0 of the warp's input ring
     unsigned char* ring0;     // row 0 of the warp's input ring
     unsigned char* plane;     // the warp's level-1 planes (low bytes, then high bytes at + PLANE)
     unsigned char* pw;        // this lane's store position in the low plane
     const unsigned char* pl;  // this lane's operand bytes in the low plane
-    int e_in, e_l1;           // ring / plane byte index of the first byte right of the row end (pixel w: reflected from w - 2), or -1
-    int own2;                 // level-2 values this warp publishes (<= OWN2; 0 if none)
-    bool last2;               // this warp holds the right end of the level-2 row
-    uint32_t bar0;            // shared address of mbarrier 0
+    // frame borders inside this warp's rows: index of pixel 0 (left border present if >= 6) / of pixel w (right, -1 if outside)
+    int in0, ine, l10, l1e;
+    bool inL, l1L;
+    int B[MAXL + 1];          // first computed pixel of level l (2..L)
+    int own_lo, own_hi;       // final-level pixels this warp stores: [own_lo, own_hi)
     uint32_t wbar;            // shared address of the warp's group-0 "rows landed" barrier
     // the warp's input ring: consumer side (all lanes) and producer side (lane 0); unit = group of two rows
     int c_g, c_phase, g_cons;
@@ -176,19 +176,14 @@ struct Stream {
     int g_int0, g_int1, box_y0;                   // groups [g_int0, g_int1) lie inside the frame: one TMA box at row box_y0 + 2 G
     uint32_t ring_u32;                            // shared address of the warp's input ring
     int src_off, cp_bytes, dst_off, box_x;        // the warp's byte range of an input row
-    // Rows of level 2 are numbered across segments (dn = rows published so far, the same in every
-    // warp).  Row barrier n % RS, phase n / RS: every warp has written its part of row n.
-    // Duty barrier n % RS, phase n / RS: the upper levels have consumed row n.
-    int dn, seg_n0, seg_q0;
-    int duty_m, turn_w, turn_c;        // next row handed to run_duty, and the warp whose turn it is
     const uint8_t* frame;
     float* out_frame;
-    int nextr[3], lastr[3];            // levels 1, 2 (levels >= 3: DutyState)
-    int seg_next[VHR_MAX_LEVELS + 1], seg_last[VHR_MAX_LEVELS + 1];
-    uint32_t VA[6], VC[6];             // level-1 vertical pass (packed pairs): partial sum of the next row, last input row
+    int nextr[MAXL + 1], lastr[MAXL + 1];         // next / last row of each level in the current segment
+    int hslot[MAXL + 1];                          // newest row of the H ring of levels >= 3
+    uint32_t VA[6], VC[6];                        // level-1 vertical pass (packed pairs): partial sum of the next row, last input row
 
-    __device__ Stream(const MmaArgs& a_, const CUtensorMap* tm, unsigned char* s)
-        : a(a_), tmap(tm), smem(s), warp((int)(threadIdx.x >> 5)), lane((int)(threadIdx.x & 31)) {
+    __device__ Pipe(const MmaArgs& a_, const CUtensorMap* tm, unsigned char* s, int strip_)
+        : a(a_), tmap(tm), wsm(s), lane((int)(threadIdx.x & 31)), strip(strip_) {
         const int g = lane >> 2, q = lane & 3;
 #pragma unroll
         for (int ph = 0; ph < 3; ++ph)
@@ -196,42 +191,38 @@ struct Stream {
             for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
                 for (int r = 0; r < 4; ++r) AF[ph][ks][r] = weight_reg(ph, ks, r, lane);
-        ring0 = smem + a.in_off + warp * a.ng * GBYTES;
-        // level-1 block J (0..23) of the warp = values [360 w - 8 + 16 J, + 16): window = ring bytes [8 + 32 J, + 64);
-        // MMA group G (0..2) takes the blocks J = 3 n + G in its columns n = g.
+#pragma unroll
+        for (int l = 2; l <= MAXL; ++l) B[l] = a.step[l] * strip + a.boff[l];
+        // level-2 value index of the first computed value: O2 = 3 B2 (levels == 1: a virtual level 2 with B2 = 60 strip);
+        // level-1 block J (0..23) = values [2 O2 - 8 + 16 J, + 16): window = input bytes [4 O2 - 24 + 32 J, + 64)
+        //   = ring bytes [8 + 32 J, + 64) with ring byte b <-> input byte 4 O2 - 32 + b;  MMA group G takes J = 3 n + G.
+        const int O2 = 3 * B[2];
+        ring0 = wsm + a.in_off;
         rd = ring0 + 8 + 96 * g + 8 * q;
-        plane = smem + a.plane_off + warp * 2 * PLANE;
+        plane = wsm + a.plane_off;
         pw = plane + 96 * q + 2 * g;                         // value pair (2 g, 2 g + 1) of block 3 (2 q + e) + G: + 48 e + 16 G
         pl = plane + 96 * (g & 3) + 8 * q;                   // level-2 block J2 = 3 (g & 3) + G: window = plane bytes [32 J2, + 64)
-        bar0 = smem_u32(smem);
-        wbar = bar0 + 8 * warp * a.ng;
+        wbar = smem_u32(wsm);
         c_g = 0; c_phase = 0; g_cons = 0; p_g = 0; g_issued = 0; g_total = 0; vg0 = 0;
         g_int0 = 0; g_int1 = 0; box_y0 = 0;
         ring_u32 = smem_u32(ring0);
-        // ring-row byte b of the warp <-> byte 24 * LANES * warp - 32 + b of the input row
-        const int lo = 24 * LANES * warp - 32;
-        box_x = lo / 4;                                   // (uint32 elements; negative = zero-filled by the TMA unit)
+        const int lo = 4 * O2 - 32;                          // input byte of ring byte 0 (a multiple of 16: B2 % 4 == 0)
+        box_x = lo / 4;                                      // (uint32 elements; outside the row = zero-filled by the TMA unit)
         src_off = max(lo, 0);
         dst_off = src_off - lo;
         cp_bytes = min(a.rowbytes, lo + WSLOT) - src_off;
-        e_in = a.rowbytes - lo;
-        if (e_in < 6 || e_in + 3 > WSLOT) e_in = -1;
-        e_l1 = 3 * a.w[1] - (12 * LANES * warp - 8);
-        if (e_l1 < 6 || e_l1 + 3 > PLANE) e_l1 = -1;
-        if constexpr (L >= 2) {
-            own2 = min(OWN2, 3 * a.w[2] - OWN2 * warp);
-            last2 = own2 > 0 && OWN2 * (warp + 1) >= 3 * a.w[2];
-        } else {
-            own2 = min(2 * OWN2, 3 * a.w[1] - 2 * OWN2 * warp);      // level-1 values written by this warp
-            last2 = false;
-        }
-        if (own2 < 0) own2 = 0;
-        dn = 0; seg_n0 = 0; seg_q0 = 0;
-        duty_m = 0; turn_w = 0; turn_c = 0;
+        in0 = -lo;          inL = in0 >= 6 && in0 + 9 <= WSLOT;
+        ine = a.rowbytes - lo;
+        if (ine < 6 || ine + 3 > WSLOT) ine = -1;
+        const int L1base = 2 * O2 - 8;
+        l10 = -L1base;      l1L = l10 >= 6 && l10 + 9 <= PLANE;
+        l1e = 3 * a.w[1] - L1base;
+        if (l1e < 6 || l1e + 3 > PLANE) l1e = -1;
+        own_lo = a.own * strip;
+        own_hi = min(own_lo + a.own, a.w[L]);
+#pragma unroll
+        for (int l = 0; l <= MAXL; ++l) { nextr[l] = 0; lastr[l] = -1; hslot[l] = 0; }
     }
-    __device__ __forceinline__ DutyState* duty_state() const { return reinterpret_cast<DutyState*>(smem + a.duty_off); }
-    __device__ __forceinline__ void wait_row(int n) { mbar_wait(bar0 + a.rbar_off + 8 * (n & (RS - 1)), (uint32_t)((n / RS) & 1)); }
-    __device__ __forceinline__ void wait_duty(int n) { mbar_wait(bar0 + a.rbar_off + 8 * (RS + (n & (RS - 1))), (uint32_t)((n / RS) & 1)); }
 
     // ---- the warp's input ring ------------------------------------------------------------------
     // Group G of a segment = virtual input rows vg0 + 2G, vg0 + 2G + 1 (reflect-101 at the frame's
@@ -255,31 +246,23 @@ struct Stream {
         p_g = (p_g + 1 == a.ng) ? 0 : p_g + 1;
     }
     // Every group the warp has consumed so far has been read by all its lanes: lane 0 requests the
-    // next groups into those slots.  (Edge warps patched border bytes into those slots through the
+    // next groups into those slots.  (Edge strips patched border bytes into those slots through the
     // generic proxy: order those writes before the bulk copies that will overwrite them.)
     __device__ __forceinline__ void refill() {
-        if (warp == 0 || e_in >= 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (inL || ine >= 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
             const int lim = min(g_total, g_cons + a.ng);
             while (g_issued < lim) issue_group(g_issued++);
         }
     }
-    // wait for the next group of the segment; returns the offset of its first row in the warp's ring.
-    // Frame borders: pixels -2, -1 <- 2, 1 (ring bytes 26..31 <- 38..40, 35..37) and pixel W <- W - 2.
+    // wait for the next group of the segment; returns the offset of its first row in the warp's ring
     __device__ __forceinline__ int next_group() {
         mbar_wait(wbar + 8 * c_g, (uint32_t)c_phase);
         const int off = c_g * GBYTES;
-        if (warp == 0 || e_in >= 0) {                // warp-uniform
-            unsigned char* p = ring0 + off;
-            if (warp == 0 && lane < 12) {
-                const int r = lane >= 6, i = lane - 6 * r;
-                p[r * WSLOT + 26 + i] = p[r * WSLOT + (i < 3 ? 38 : 32) + i];
-            }
-            if (e_in >= 0 && lane >= 16 && lane < 22) {
-                const int r = lane >= 19, i = lane - 16 - 3 * r;
-                p[r * WSLOT + e_in + i] = p[r * WSLOT + e_in - 6 + i];
-            }
+        if (inL || ine >= 0) {                       // warp-uniform: frame borders of the two input rows
+            patch_row(ring0 + off, in0, inL, ine, ine >= 0, lane);
+            patch_row(ring0 + off + WSLOT, in0, inL, ine, ine >= 0, lane);
             __syncwarp();
         }
         ++g_cons;
@@ -298,8 +281,8 @@ struct Stream {
         for (int k = 0; k < 4; ++k) b[k] = *reinterpret_cast<const uint2*>(p + 32 * k);
 #pragma unroll
         for (int G = 0; G < 3; ++G) {
-            int d[4] = {0, 0, 0, 0};
-            imma(d, AF[(PH0 + G) % 3][0], b[G].x, b[G].y);
+            int d[4];
+            imma0(d, AF[(PH0 + G) % 3][0], b[G].x, b[G].y);
             imma(d, AF[(PH0 + G) % 3][1], b[G + 1].x, b[G + 1].y);
             pk[2 * G] = (uint32_t)d[0] + ((uint32_t)d[2] << 16);
             pk[2 * G + 1] = (uint32_t)d[1] + ((uint32_t)d[3] << 16);
@@ -344,15 +327,9 @@ struct Stream {
             *reinterpret_cast<uint16_t*>(d + PLANE) = (uint16_t)__byte_perm(v[k], 0u, 0x4431);    // high bytes
         }
         __syncwarp();
-        if (warp == 0 || e_l1 >= 0) {                // frame borders of level 1: values -6..-1 <- 6..8, 3..5; pixel w1 <- w1 - 2
-            if (warp == 0 && lane < 12) {
-                const int h = lane >= 6, i = lane - 6 * h;
-                plane[h * PLANE + 2 + i] = plane[h * PLANE + (i < 3 ? 14 : 8) + i];
-            }
-            if (e_l1 >= 0 && lane >= 16 && lane < 22) {
-                const int h = lane >= 19, i = lane - 16 - 3 * h;
-                plane[h * PLANE + e_l1 + i] = plane[h * PLANE + e_l1 - 6 + i];
-            }
+        if (l1L || l1e >= 0) {                       // frame borders of level 1 (both planes)
+            patch_row(plane, l10, l1L, l1e, l1e >= 0, lane);
+            patch_row(plane + PLANE, l10, l1L, l1e, l1e >= 0, lane);
             __syncwarp();
         }
         uint2 bl[4], bh[4];
@@ -363,10 +340,10 @@ struct Stream {
         }
 #pragma unroll
         for (int G = 0; G < 3; ++G) {
-            int dl[4] = {0, 0, 0, 0}, dh[4] = {0, 0, 0, 0};
-            imma(dl, AF[G][0], bl[G].x, bl[G].y);
+            int dl[4], dh[4];
+            imma0(dl, AF[G][0], bl[G].x, bl[G].y);
             imma(dl, AF[G][1], bl[G + 1].x, bl[G + 1].y);
-            imma(dh, AF[G][0], bh[G].x, bh[G].y);
+            imma0(dh, AF[G][0], bh[G].x, bh[G].y);
             imma(dh, AF[G][1], bh[G + 1].x, bh[G + 1].y);
 #pragma unroll
             for (int i = 0; i < 4; ++i) x[4 * G + i] = dl[i] + (dh[i] << 8);     // < 2^20
@@ -382,15 +359,13 @@ struct Stream {
         frame = a.frames + (size_t)t * a.H * a.rowbytes;
         out_frame = a.out + (size_t)t * a.h[L] * a.w[L] * 3;
         int f = r0, e = r1 - 1;
-        seg_next[L] = f; seg_last[L] = e;
+        nextr[L] = f; lastr[L] = e;
 #pragma unroll
         for (int l = L - 1; l >= 1; --l) {
             f = max(0, 2 * f - 2);
             e = min(a.h[l] - 1, 2 * e + 2);
-            seg_next[l] = f; seg_last[l] = e;
+            nextr[l] = f; lastr[l] = e;
         }
-        nextr[1] = seg_next[1]; lastr[1] = seg_last[1];
-        if constexpr (L >= 2) { nextr[2] = seg_next[2]; lastr[2] = seg_last[2]; }
         // input rows of the segment: virtual rows 2*first-2 .. 2*last+2 in groups of two, after one filler row
         vg0 = 2 * nextr[1] - 3;
         g_total = (lastr[1] - nextr[1] + 1) + 2;
@@ -399,74 +374,34 @@ struct Stream {
         g_int0 = vg0 < 0 ? (1 - vg0) / 2 : 0;                 // first G with vg0 + 2G >= 0
         g_int1 = (a.H - vg0) / 2;                            // first G with vg0 + 2G + 1 >= H  (vg0 odd)
         box_y0 = t * a.H + vg0;
-        seg_n0 = dn;
-        seg_q0 = (L >= 2) ? nextr[L >= 2 ? 2 : 1] : 0;
     }
 
-    // ---- levels >= 3, run by ONE warp per level-2 row (the warps take turns) --------------------
-    // Row r of level l-1 is complete in ring l-1.  Level 2 (the source of l = 3): slot r % RS, interleaved, pixel p
-    // channel c at float 3 (p + 2) + c (aprons px -2, -1 in front, px w behind).  Levels >= 3: slot r & 1, per
-    // channel plane, aprons at float 2, 3 = px -2, -1, px p at float 4 + p, aprons px w, w + 1 behind.  A lane owns
-    // N = 64 >> l adjacent pixels of level l: horizontal pass into the H ring of level l (HR rows), then every
-    // level-l row whose five H rows are present is finished, written to ring l (or to global memory at the last
-    // level) and handed to level l+1 by the same warp: no block barrier anywhere above level 2.
+    // ---- levels >= 3, inline in the same warp: one lane per pixel (3 channels) ---------------------------------------
+    // Row r of level l-1 sits in the warp's strip of that level (interleaved floats, pixel B[l-1] + i at float 3 i).
+    // Horizontal pass of the warp's ncomp(l) pixels into the H ring of level l (HR rows), then every level-l row whose
+    // five H rows are present is finished (reflect-101 at the frame's top / bottom), written to the strip of level l
+    // (or, at the last level, to global memory: the owned pixels only) and handed to level l+1.
     template <int l>
-    __device__ __forceinline__ void duty_row(int r, int src_slot) {
-        constexpr int N = 64 >> l;                 // 8, 4, 2, 1 pixels per lane
-        constexpr int C = N >= 4 ? 4 : N;          // pixels per vertical-pass chunk
-        DutyState* ds = duty_state();
-        const int wl = a.w[l], hp = a.h[l - 1];
-        int hs = ds->hslot[l] + 1;
+    __device__ __forceinline__ void upper(int r) {
+        constexpr int NL = ncomp(l);
+        const int hp = a.h[l - 1], wl = a.w[l];
+        int hs = hslot[l] + 1;
         if (hs == HR) hs = 0;
-        float* const hring = reinterpret_cast<float*>(smem + a.hring_off[l]);
-        if constexpr (l == 3) {
-            // source = level-2 ring row, interleaved; a lane's 8 pixels in two halves of 4 (12 source pixels = 9 x LDS.128 each)
-            const float* const src = reinterpret_cast<const float*>(smem + a.ring_off[2]) + src_slot * a.ring_stride[2];
-            for (int px0 = lane * N; px0 < wl; px0 += 32 * N) {
+        float* const hring = reinterpret_cast<float*>(wsm + a.hring_off[l]);
+        const float* const src = reinterpret_cast<const float*>(wsm + a.strip_off[l - 1]);
+        // pixel B[l] + lane of level l reads pixels 2 (B[l] + lane) - 2 + d of level l-1 = strip pixel 2 lane + d + off
+        const int off = 2 * B[l] - 2 - B[l - 1];
+        if (lane < NL) {
+            const float* p = src + 3 * (2 * lane + off);
+            float o[3];
 #pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-                    float x[36];                    // px 2 (px0 + 4 hf) - 2 .. + 11, interleaved (the last px is not used)
-                    const float* p = src + 6 * (px0 + 4 * hf);
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) ldv<4>(p + 4 * k, x + 4 * k);
-#pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) {
-                        float o[4];
-#pragma unroll
-                        for (int m = 0; m < 4; ++m)
-                            o[m] = x[3 * (2 * m + 2) + ch] * 6.0f + (x[3 * (2 * m + 1) + ch] + x[3 * (2 * m + 3) + ch]) * 4.0f +
-                                   x[3 * (2 * m) + ch] + x[3 * (2 * m + 4) + ch];
-                        stv<4>(hring + (hs * 3 + ch) * wl + px0 + 4 * hf, o);
-                    }
-                }
-            }
-        } else {
-            const float* const src = reinterpret_cast<const float*>(smem + a.ring_off[l - 1]) + src_slot * 3 * a.ring_stride[l - 1];
-            for (int px0 = lane * N; px0 < wl; px0 += 32 * N) {
-#pragma unroll
-                for (int ch = 0; ch < 3; ++ch) {
-                    const float* p = src + ch * a.ring_stride[l - 1] + 2 * px0 + 2;     // px 2 px0 - 2
-                    float x[2 * N + 4];
-                    ldv<2>(p, x);
-                    if constexpr (N >= 2) {
-#pragma unroll
-                        for (int k = 0; k < N / 2; ++k) ldv<4>(p + 2 + 4 * k, x + 2 + 4 * k);
-                    } else {
-                        ldv<2>(p + 2, x + 2);
-                    }
-                    x[2 * N + 2] = p[2 * N + 2];
-                    float o[N];
-#pragma unroll
-                    for (int m = 0; m < N; ++m)
-                        o[m] = x[2 * m + 2] * 6.0f + (x[2 * m + 1] + x[2 * m + 3]) * 4.0f + x[2 * m] + x[2 * m + 4];
-                    float* hd = hring + (hs * 3 + ch) * wl + px0;
-#pragma unroll
-                    for (int k = 0; k < N; k += C) stv<C>(hd + k, o + k);
-                }
-            }
+            for (int ch = 0; ch < 3; ++ch)
+                o[ch] = p[6 + ch] * 6.0f + (p[3 + ch] + p[9 + ch]) * 4.0f + p[ch] + p[12 + ch];
+            float* hd = hring + (hs * NL + lane) * 3;
+            hd[0] = o[0]; hd[1] = o[1]; hd[2] = o[2];
         }
-        int nx = ds->nextr[l];
-        const int lst = ds->lastr[l];
+        int nx = nextr[l];
+        const int lst = lastr[l];
         __syncwarp();
         while (nx <= lst && min(2 * nx + 2, hp - 1) <= r) {
             const int q = nx;
@@ -475,146 +410,96 @@ struct Stream {
             for (int d = 0; d < 5; ++d) {
                 int sl = hs - (r - vhr_reflect101(2 * q - 2 + d, hp));
                 if (sl < 0) sl += HR;
-                so[d] = sl * 3 * wl;
+                so[d] = sl * NL * 3;
             }
-            float* const dring = (l < L) ? reinterpret_cast<float*>(smem + a.ring_off[l < L ? l : 3]) + (q & 1) * 3 * a.ring_stride[l < L ? l : 3] : nullptr;
-            for (int px0 = lane * C; px0 < wl; px0 += 32 * C) {
-                float v[3][C];
+            if (lane < NL) {
+                const float* hc = hring + 3 * lane;
+                float v[3];
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) {
-                    const float* hc = hring + ch * wl + px0;
-                    float t0[C], t1[C], t2[C], t3[C], t4[C];
-                    ldv<C>(hc + so[0], t0); ldv<C>(hc + so[1], t1); ldv<C>(hc + so[2], t2);
-                    ldv<C>(hc + so[3], t3); ldv<C>(hc + so[4], t4);
-#pragma unroll
-                    for (int m = 0; m < C; ++m)
-                        v[ch][m] = (t2[m] * 6.0f + (t1[m] + t3[m]) * 4.0f + t0[m] + t4[m]) * (1.0f / 256.0f);
-                }
+                for (int ch = 0; ch < 3; ++ch)
+                    v[ch] = (hc[so[2] + ch] * 6.0f + (hc[so[1] + ch] + hc[so[3] + ch]) * 4.0f + hc[so[0] + ch] + hc[so[4] + ch]) * (1.0f / 256.0f);
                 if constexpr (l == L) {
-                    float t[3 * C];
-#pragma unroll
-                    for (int m = 0; m < C; ++m) { t[3 * m] = v[0][m]; t[3 * m + 1] = v[1][m]; t[3 * m + 2] = v[2][m]; }
-                    float* o = out_frame + ((size_t)q * wl + px0) * 3;
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) stv<C>(o + C * k, t + C * k);
+                    const int px = B[l] + lane;
+                    if (px >= own_lo && px < own_hi) {
+                        float* o = out_frame + ((size_t)q * wl + px) * 3;
+                        o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
+                    }
                 } else {
-#pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) stv<C>(dring + ch * a.ring_stride[l] + 4 + px0, v[ch]);
+                    float* sd = reinterpret_cast<float*>(wsm + a.strip_off[l]) + 3 * lane;
+                    sd[0] = v[0]; sd[1] = v[1]; sd[2] = v[2];
                 }
             }
             nx = q + 1;
             if constexpr (l < L) {
                 __syncwarp();
-                if (lane < 3) {                     // reflect-101 aprons of the new row, one channel per lane
-                    float* pa = dring + lane * a.ring_stride[l];
-                    pa[2] = pa[4 + vhr_reflect101(-2, wl)];
-                    pa[3] = pa[4 + vhr_reflect101(-1, wl)];
-                    pa[4 + wl] = pa[4 + vhr_reflect101(wl, wl)];
-                    pa[5 + wl] = pa[4 + vhr_reflect101(wl + 1, wl)];
+                const int i0 = -3 * B[l], ie = 3 * (wl - B[l]);
+                const bool lf = i0 >= 6 && i0 + 9 <= 3 * NL, rt = ie >= 6 && ie + 3 <= 3 * NL;
+                if (lf || rt) {                      // frame borders of level l
+                    patch_row(reinterpret_cast<float*>(wsm + a.strip_off[l]), i0, lf, ie, rt, lane);
+                    __syncwarp();
                 }
-                __syncwarp();
-                duty_row<l + 1>(q, q & 1);
+                upper<l + 1>(q);
             }
         }
         __syncwarp();
-        if (lane == 0) { ds->hslot[l] = hs; ds->nextr[l] = nx; }
+        hslot[l] = hs;
+        nextr[l] = nx;
     }
 
-    // Upper levels of the next level-2 row (number duty_m), by the warp whose turn it is.  Turns
-    // rotate with a skew (warp (n + n / nw) % nw) so that the heavier rows, which also finish rows
-    // of the upper levels, do not always fall on the same warps.  The row must be complete and the
-    // previous row's upper-level work done (shared H rings, DutyState).
-    // Every parity wait below lags its barrier by less than one phase: the next phase of row
-    // barrier n % RS needs this warp's signal for row n + RS, which follows duty(n) in program
-    // order via the slot wait in publish(); the next phase of duty barrier (n-1) % RS needs duty(n).
-    __device__ __forceinline__ void run_duty() {
-        if constexpr (L >= 3) {
-            const int n = duty_m;
-            if (turn_w == warp) {
-                wait_row(n);
-                if (n >= 1) wait_duty(n - 1);
-                duty_row<3>(seg_q0 + (n - seg_n0), n & (RS - 1));
-                __syncwarp();
-                if (lane == 0)
-                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar0 + a.rbar_off + 8 * (RS + (n & (RS - 1)))) : "memory");
-            }
-            const int nw = blockDim.x >> 5;
-            duty_m = n + 1;
-            ++turn_w;
-            if (++turn_c == nw) { turn_c = 0; ++turn_w; }
-            if (turn_w >= nw) turn_w -= nw;
-            if (turn_w >= nw) turn_w -= nw;
-        }
-    }
     // A finished level-2 row: this lane holds 12 sums (exact, < 2^24) of which the lanes with q < 2 are real (the
-    // MMA columns 4..7 of level 2 are duplicates): value x[4 G + e + 2 h] = level-2 value 96 q + 48 e + 16 G + 2 g + h
-    // of the warp's 192-value window.
-    __device__ __forceinline__ void publish(int q, const int (&s)[12]) {
-        const int n = dn;
-        if constexpr (L >= 3) {
-            // the ring slot's previous row (n - RS) has been consumed; this also keeps the signals of
-            // row n out of the row barrier's previous phase
-            if (n >= RS) wait_duty(n - RS);
+    // MMA columns 4..7 of level 2 are duplicates): value s[4 G + e + 2 h] = level-2 value 96 q + 48 e + 16 G + 2 g + h
+    // of the warp's 192-value window (the first 180 = 60 pixels are valid).
+    __device__ __forceinline__ void emit2(int q, const int (&s)[12]) {
+        float* dst;
+        int jlo, jhi;                                // values of the window to store
+        if constexpr (L == 2) {
+            dst = out_frame + ((size_t)q * a.w[2] + B[2]) * 3;
+            jlo = 3 * (own_lo - B[2]); jhi = 3 * (own_hi - B[2]);
+        } else {
+            dst = reinterpret_cast<float*>(wsm + a.strip_off[2]);
+            jlo = 0; jhi = 3 * N2;
         }
-        {
-            float* dst;
-            if constexpr (L == 2) dst = out_frame + (size_t)q * a.w[2] * 3 + OWN2 * warp;
-            else dst = reinterpret_cast<float*>(smem + a.ring_off[2]) + (n & (RS - 1)) * a.ring_stride[2] + 6 + OWN2 * warp;
-            const int j0 = 96 * (lane & 3) + 2 * (lane >> 2);
-            if ((lane & 3) < 2) {
+        const int j0 = 96 * (lane & 3) + 2 * (lane >> 2);
+        if ((lane & 3) < 2) {
 #pragma unroll
-                for (int G = 0; G < 3; ++G)
+            for (int G = 0; G < 3; ++G)
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int j = j0 + 48 * e + 16 * G;
-                        if (j < own2)
-                            *reinterpret_cast<float2*>(dst + j) = make_float2((float)s[4 * G + e] * (1.0f / 65536.0f),
-                                                                              (float)s[4 * G + e + 2] * (1.0f / 65536.0f));
-                    }
-            }
-            if constexpr (L >= 3) {
-                if (warp == 0 || last2) {            // aprons: px -2 <- px 2, px -1 <- px 1, px w2 <- px w2 - 2
-                    __syncwarp();
-                    float* row = reinterpret_cast<float*>(smem + a.ring_off[2]) + (n & (RS - 1)) * a.ring_stride[2];
-                    if (warp == 0 && lane < 6) row[lane] = row[(lane < 3 ? 12 : 6) + lane];
-                    if (last2 && lane >= 8 && lane < 11) row[6 + 3 * a.w[2] + lane - 8] = row[3 * a.w[2] + lane - 8];
+                for (int e = 0; e < 2; ++e) {
+                    const int j = j0 + 48 * e + 16 * G;
+                    if (j >= jlo && j < jhi)
+                        *reinterpret_cast<float2*>(dst + j) = make_float2((float)s[4 * G + e] * (1.0f / 65536.0f),
+                                                                          (float)s[4 * G + e + 2] * (1.0f / 65536.0f));
                 }
-            }
         }
+        nextr[2] = q + 1;
         if constexpr (L >= 3) {
             __syncwarp();
-            if (lane == 0)
-                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar0 + a.rbar_off + 8 * (n & (RS - 1))) : "memory");
+            const int i0 = -3 * B[2], ie = 3 * (a.w[2] - B[2]);
+            const bool lf = i0 >= 6 && i0 + 9 <= 3 * N2, rt = ie >= 6 && ie + 3 <= 3 * N2;
+            if (lf || rt) {                          // frame borders of level 2
+                patch_row(dst, i0, lf, ie, rt, lane);
+                __syncwarp();
+            }
+            upper<3>(q);
         }
-        dn = n + 1;
-        nextr[2] = q + 1;
-        if (n - DLY >= seg_n0) run_duty();           // an older row: complete by now, and nobody waits for its upper levels yet
     }
 
     // ---- one segment ----------------------------------------------------------------------------
     __device__ __forceinline__ void run_segment() {
-        __syncthreads();                // every warp is done with the previous segment (upper levels included)
-        if constexpr (L >= 3) {
-            if (threadIdx.x == 0) {
-                DutyState* ds = duty_state();
-#pragma unroll
-                for (int l = 3; l <= L; ++l) { ds->nextr[l] = seg_next[l]; ds->lastr[l] = seg_last[l]; }
-            }
-            __syncthreads();
-        }
         refill();
         prime();
         if constexpr (L == 1) {
             int n = 0;
-            const int j0 = 96 * (lane & 3) + 2 * (lane >> 2) - 8;            // first value of the lane's pairs, relative to the owned range
+            // the lane's pairs: level-1 value 2 O2 - 8 + 96 q + 48 e + 16 G + 2 g (+1); stored if its pixel is owned
+            const int v0 = 6 * B[2] - 8 + 96 * (lane & 3) + 2 * (lane >> 2);
             for (int r = nextr[1]; r <= lastr[1]; ++r) {
                 uint32_t v[6];
                 l1_row(v);
-                float* o = out_frame + (size_t)r * a.w[1] * 3 + 2 * OWN2 * warp;
+                float* o = out_frame + (size_t)r * a.w[1] * 3;
 #pragma unroll
                 for (int k = 0; k < 6; ++k) {
-                    const int j = j0 + 48 * (k & 1) + 16 * (k >> 1);
-                    if (j >= 0 && j < own2)
+                    const int j = v0 + 48 * (k & 1) + 16 * (k >> 1);
+                    if (j >= 3 * own_lo && j < 3 * own_hi)
                         *reinterpret_cast<float2*>(o + j) = make_float2((float)(v[k] & 0xFFFFu) * (1.0f / 256.0f),
                                                                         (float)(v[k] >> 16) * (1.0f / 256.0f));
                 }
@@ -624,9 +509,10 @@ struct Stream {
             const int h1 = a.h[1];
             int q = nextr[2];
             const int ql = lastr[2];
-            // level-2 vertical pass, incremental: A = r(2q-2) + 4 r(2q-1) + 6 r(2q), B = 4 r(2q-1) + r(2q-2), C = r(2q)
-            // (r = the level-2 horizontal sums of a level-1 row); rows 0 .. 2 prime it at the top of a frame
-            int A[12], B[12], C[12];
+            // level-2 vertical pass, incremental: A = r(2q-2) + 4 r(2q-1) + 6 r(2q), C = r(2q)  (r = the level-2 horizontal
+            // sums of a level-1 row); rows 0 .. 2 prime it at the top of a frame.  Bottom border: the rows that reflect
+            // are 4 r(2q-1) + r(2q-2) = A - 6 C.
+            int A[12], C[12];
             {
                 int x0[12], x1[12];
                 l12_row(x0);
@@ -639,14 +525,11 @@ struct Stream {
                     int s[12];
 #pragma unroll
                     for (int k = 0; k < 12; ++k) s[k] = 6 * x0[k] + 8 * x1[k] + 2 * C[k];
-                    publish(0, s);
+                    emit2(0, s);
                     q = 1;
                 }
 #pragma unroll
-                for (int k = 0; k < 12; ++k) {
-                    B[k] = 4 * x1[k] + x0[k];
-                    A[k] = B[k] + 6 * C[k];
-                }
+                for (int k = 0; k < 12; ++k) A[k] = x0[k] + 4 * x1[k] + 6 * C[k];
             }
 #pragma unroll 1
             for (; q <= ql; ++q) {
@@ -660,14 +543,14 @@ struct Stream {
 #pragma unroll
                         for (int k = 0; k < 12; ++k) {
                             s[k] = A[k] + 4 * n1[k];
-                            B[k] = 4 * n1[k] + C[k];
+                            A[k] = 4 * n1[k] + C[k];
                         }
                     }
                     l12_row(C);
 #pragma unroll
                     for (int k = 0; k < 12; ++k) {
                         s[k] += C[k];
-                        A[k] = B[k] + 6 * C[k];
+                        A[k] += 6 * C[k];
                     }
                 } else if (has1) {                   // row 2q+2 = h1 reflects to 2q
                     int n1[12];
@@ -676,40 +559,34 @@ struct Stream {
                     for (int k = 0; k < 12; ++k) s[k] = A[k] + 4 * n1[k] + C[k];
                 } else {                             // rows 2q+1, 2q+2 reflect to 2q-1, 2q-2
 #pragma unroll
-                    for (int k = 0; k < 12; ++k) s[k] = A[k] + B[k];
+                    for (int k = 0; k < 12; ++k) s[k] = 2 * A[k] - 6 * C[k];
                 }
                 refill();
-                publish(q, s);
+                emit2(q, s);
             }
-            while (duty_m < dn) run_duty();          // the last rows of the segment
         }
     }
 };
 
-template <int L, int MAXT>
-__global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) pyrdown_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap) {
+template <int L>
+__global__ void __launch_bounds__(256, 2) pyrdown_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const long long lo = a.total_rows * blockIdx.x / gridDim.x;
-    const long long hi = a.total_rows * (blockIdx.x + 1) / gridDim.x;
+    const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
+    const int cg = (int)(blockIdx.x % a.ncg), share = (int)(blockIdx.x / a.ncg), nshares = (int)(gridDim.x / a.ncg);
+    const int strip = cg * a.wpc + warp;
+    if (strip >= a.strips || share >= nshares) return;           // (warps never synchronise with one another)
+    const long long lo = a.total_rows * share / nshares;
+    const long long hi = a.total_rows * (share + 1) / nshares;
     if (lo >= hi) return;
-    if (threadIdx.x == 0) {
-        const int nw = blockDim.x >> 5;
-        for (int b = 0; b < nw * a.ng; ++b) mbar_init(smem_u32(smem) + 8 * b, 1);             // rows landed, per warp and group
-        for (int b = 0; b < RS; ++b) {
-            mbar_init(smem_u32(smem) + a.rbar_off + 8 * b, nw);                                // row barriers: one arrival per warp
-            mbar_init(smem_u32(smem) + a.rbar_off + 8 * (RS + b), 1);                          // duty barriers: one arrival per row
-        }
-        DutyState* ds = reinterpret_cast<DutyState*>(smem + a.duty_off);
-        for (int l = 0; l <= VHR_MAX_LEVELS; ++l) { ds->hslot[l] = 0; ds->nextr[l] = 0; ds->lastr[l] = -1; }
+    unsigned char* wsm = smem + (size_t)warp * a.warp_smem;
+    if (lane == 0) {
+        for (int b = 0; b < a.ng; ++b) mbar_init(smem_u32(wsm) + 8 * b, 1);                  // rows landed, per group
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // the level-1 planes are read 64 bytes per block window: clear them once so that never-written tail bytes are defined
-    {
-        const int nw = blockDim.x >> 5;
-        uint32_t* pz = reinterpret_cast<uint32_t*>(smem + a.plane_off);
-        for (int i = threadIdx.x; i < nw * 2 * PLANE / 4; i += blockDim.x) pz[i] = 0u;
-    }
-    Stream<L> st(a, &tmap, smem);
+    for (int i = lane; i < 2 * PLANE / 4; i += 32) reinterpret_cast<uint32_t*>(wsm + a.plane_off)[i] = 0u;
+    __syncwarp();
+    Pipe<L> st(a, &tmap, wsm, strip);
     const int hL = a.h[L];
     long long pos = lo;
     while (pos < hi) {
@@ -718,35 +595,24 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) pyrdown_mma_kernel(
         const long long frame_end = (long long)(t + 1) * hL;
         const int r1 = (int)((hi < frame_end ? hi : frame_end) - (long long)t * hL);
         st.begin_segment(t, r0, r1);
-        st.run_segment();               // starts with a block barrier: the previous segment's shared rows are dead
+        st.run_segment();
         pos += r1 - r0;
     }
 }
 
-template <int L, int MAXT>
+template <int L>
 int launch_mma(vhr_ctx* ctx, const MmaArgs& a, const CUtensorMap& tmap, int threads, int smem_bytes, cudaStream_t stream) {
-    auto kern = pyrdown_mma_kernel<L, MAXT>;
+    auto kern = pyrdown_mma_kernel<L>;
     VHR_CHECK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     int per_sm = 0;
     VHR_CHECK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem_bytes));
     if (per_sm < 1) return VHR_ERR_UNSUPPORTED;
-    long long grid = (long long)per_sm * ctx->num_sms;
-    if (grid > a.total_rows) grid = a.total_rows;
-    kern<<<(int)grid, threads, smem_bytes, stream>>>(a, tmap);
+    long long resident = (long long)per_sm * ctx->num_sms;
+    long long nshares = resident / a.ncg;
+    if (nshares < 1) nshares = 1;
+    if (nshares > a.total_rows) nshares = a.total_rows;
+    kern<<<(unsigned)(nshares * a.ncg), threads, smem_bytes, stream>>>(a, tmap);
     return vhr_after_launch(ctx, "pyrdown_mma_kernel");
-}
-
-template <int MAXT>
-int dispatch_mma(vhr_ctx* ctx, const MmaArgs& a, const CUtensorMap& tmap, int threads, int smem_bytes, cudaStream_t stream) {
-    switch (a.levels) {
-        case 1: return launch_mma<1, MAXT>(ctx, a, tmap, threads, smem_bytes, stream);
-        case 2: return launch_mma<2, MAXT>(ctx, a, tmap, threads, smem_bytes, stream);
-        case 3: return launch_mma<3, MAXT>(ctx, a, tmap, threads, smem_bytes, stream);
-        case 4: return launch_mma<4, MAXT>(ctx, a, tmap, threads, smem_bytes, stream);
-        case 5: return launch_mma<5, MAXT>(ctx, a, tmap, threads, smem_bytes, stream);
-        case 6: return launch_mma<6, MAXT>(ctx, a, tmap, threads, smem_bytes, stream);
-    }
-    return VHR_ERR_INVALID;
 }
 
 }  // namespace
@@ -754,59 +620,68 @@ int dispatch_mma(vhr_ctx* ctx, const MmaArgs& a, const CUtensorMap& tmap, int th
 // Returns VHR_ERR_UNSUPPORTED (without setting an error) when the shape is not eligible.
 int vhr_pyrdown_mma(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int W, int levels, float* d_level,
                     cudaStream_t stream) {
-    if (W % 16 != 0 || W > 8 * LANES * 16 || (reinterpret_cast<uintptr_t>(d_frames) & 15) != 0 ||
+    if (levels > MAXL || W % 16 != 0 || W % (1 << levels) != 0 || (reinterpret_cast<uintptr_t>(d_frames) & 15) != 0 ||
         (reinterpret_cast<uintptr_t>(d_level) & 15) != 0)
         return VHR_ERR_UNSUPPORTED;
-    if (levels >= 3 && W % 64 != 0) return VHR_ERR_UNSUPPORTED;     // a lane of the upper-level warp owns 64 >> l pixels
     MmaArgs a;
     memset(&a, 0, sizeof(a));
     a.frames = d_frames; a.out = d_level; a.T = T; a.H = H; a.W = W; a.levels = levels;
     PyrDims d = vhr_make_dims(W, H, levels);
     for (int l = 0; l <= VHR_MAX_LEVELS; ++l) { a.w[l] = d.w[l]; a.h[l] = d.h[l]; }
     if (levels == 1 ? H < 2 : a.h[1] < 3) return VHR_ERR_UNSUPPORTED;   // the vertical passes are primed with three rows
+    if (H < 8) return VHR_ERR_UNSUPPORTED;                               // reflected filler rows reach 5 rows outside the frame
+    if (levels >= 2 && a.w[levels - 1] < 4) return VHR_ERR_UNSUPPORTED;  // border patches assume single reflections (px -2 <- 2, px w <- w - 2)
     a.total_rows = (long long)T * a.h[levels];
-    a.nt = W / 8;
     a.rowbytes = 3 * W;
-    const int warps = (a.nt + LANES - 1) / LANES;
-    const int threads = warps * 32;
+    // strip geometry: a warp computes 60 px of level 2 from pixel B2 = step2 * strip + boff2 (B2 % 4 == 0 keeps the input
+    // window 16-byte aligned), 28 / 12 / 4 px of levels 3 / 4 / 5 from B_{l+1} = ceil((B_l + 2) / 2), and owns
+    // `own` pixels of the last level (level-1 / level-2 pixels for levels 1 / 2: nothing is recomputed there)
+    static const int OWN[MAXL + 1] = {0, 120, 60, 24, 12, 4};
+    static const int STEP2[MAXL + 1] = {0, 60, 60, 48, 48, 32};
+    static const int BOFF2[MAXL + 1] = {0, 0, 0, -4, -8, -16};
+    a.own = OWN[levels];
+    a.step[2] = STEP2[levels];
+    a.boff[2] = BOFF2[levels];
+    for (int l = 3; l <= MAXL; ++l) {
+        a.step[l] = a.step[l - 1] / 2;
+        a.boff[l] = (a.boff[l - 1] + 3 + 1000) / 2 - 500;            // ceil((boff + 2) / 2), also for negative boff (the step is even)
+    }
+    for (int l = 3; l <= levels; ++l) {                              // the owned pixels must be inside the computed ones
+        const int lo_l = a.boff[l], hi_l = a.boff[l] + ncomp(l);
+        if (l == levels && (lo_l > 0 || hi_l < a.own)) return VHR_ERR_UNSUPPORTED;
+        (void)lo_l; (void)hi_l;
+    }
+    a.strips = (a.w[levels] + a.own - 1) / a.own;
+    // a CTA is a container of independent warps: 4..8 strips, as few idle warps in the last column group as possible
+    int best_wpc = 8, best_waste = 1 << 30;
+    for (int wpc = 8; wpc >= 4; --wpc) {
+        const int ncg = (a.strips + wpc - 1) / wpc;
+        const int waste = ncg * wpc - a.strips;
+        if (waste < best_waste) { best_waste = waste; best_wpc = wpc; }
+    }
+    if (a.strips < 4) best_wpc = a.strips;
+    a.wpc = best_wpc;
+    a.ncg = (a.strips + a.wpc - 1) / a.wpc;
+    const int threads = a.wpc * 32;
+    // per-warp shared memory
     auto al16 = [](int v) { return (v + 15) & ~15; };
-    int fixed = al16(warps * 2 * PLANE);                            // everything but the input rings
-    if (levels >= 3) {
-        a.ring_stride[2] = (3 * (a.w[2] + 4) + 3) & ~3;             // interleaved: px p channel c at float 3 (p + 2) + c
-        fixed = al16(fixed + RS * a.ring_stride[2] * 4);
-    }
-    for (int l = 3; l < levels; ++l) {
-        a.ring_stride[l] = (a.w[l] + 8 + 3) & ~3;                   // px p at float 4 + p; aprons at 2, 3 and w + 4, w + 5
-        fixed = al16(fixed + 2 * 3 * a.ring_stride[l] * 4);
-    }
-    for (int l = 3; l <= levels; ++l) fixed = al16(fixed + HR * 3 * a.w[l] * 4);
-    // per-warp input rings: as deep as two CTAs per SM allow (2 groups are consumed between two refills)
-    const int budget = (threads <= 256 ? ctx->smem_optin / 2 - 2048 : ctx->smem_optin - 1024);
-    int ng = 6;
     auto al128 = [](int v) { return (v + 127) & ~127; };
-    auto head = [&](int n) { return al128(al16(8 * (warps * n + 2 * RS)) + al16((int)sizeof(DutyState))); };
-    while (ng > 3 && head(ng) + warps * ng * GBYTES + fixed > budget) --ng;
-    if (head(ng) + warps * ng * GBYTES + fixed > ctx->smem_optin) return VHR_ERR_UNSUPPORTED;
+    int fixed = al16(2 * PLANE);
+    for (int l = 2; l < levels; ++l) fixed = al16(fixed + 3 * ncomp(l) * 4 + 16);
+    for (int l = 3; l <= levels; ++l) fixed = al16(fixed + HR * 3 * ncomp(l) * 4);
+    int ng = 6;                                                       // ring depth: as deep as 16 warps per SM (128 registers each) allow
+    const int ctas = 16 / a.wpc;                                      // CTAs per SM by registers
+    const int budget = 233472 / ctas - 1024 - 256;                    // 228 KB per SM, 1 KB reserved per CTA
+    while (ng > 3 && a.wpc * al128(128 + ng * GBYTES + fixed) > budget) --ng;
     a.ng = ng;
-    a.rbar_off = 8 * warps * ng;
-    a.duty_off = al16(8 * (warps * ng + 2 * RS));
-    int off = head(ng);
-    a.in_off = off;
-    off = al16(off + warps * ng * GBYTES);
-    a.plane_off = off;
-    off = al16(off + warps * 2 * PLANE);
-    if (levels >= 3) {
-        a.ring_off[2] = off;
-        off = al16(off + RS * a.ring_stride[2] * 4);
-    }
-    for (int l = 3; l < levels; ++l) {
-        a.ring_off[l] = off;
-        off = al16(off + 2 * 3 * a.ring_stride[l] * 4);
-    }
-    for (int l = 3; l <= levels; ++l) {
-        a.hring_off[l] = off;
-        off = al16(off + HR * 3 * a.w[l] * 4);
-    }
+    a.in_off = 128;                                                   // (mbarriers in the first 128 bytes)
+    a.plane_off = a.in_off + ng * GBYTES;
+    int off = al16(a.plane_off + 2 * PLANE);
+    for (int l = 2; l < levels; ++l) { a.strip_off[l] = off; off = al16(off + 3 * ncomp(l) * 4 + 16); }
+    for (int l = 3; l <= levels; ++l) { a.hring_off[l] = off; off = al16(off + HR * 3 * ncomp(l) * 4); }
+    a.warp_smem = al128(off);
+    const int smem_bytes = a.wpc * a.warp_smem;
+    if (smem_bytes > ctx->smem_optin) return VHR_ERR_UNSUPPORTED;
     // the clip as a 2-D uint32 tensor: (T*H) rows x (3W/4) elements; box = one warp's two-row group
     static PFN_cuTensorMapEncodeTiled encode = nullptr;
     if (!encode) {
@@ -827,6 +702,12 @@ int vhr_pyrdown_mma(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int W, 
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return VHR_ERR_UNSUPPORTED;
-    if (threads <= 256) return dispatch_mma<256>(ctx, a, tmap, threads, off, stream);
-    return dispatch_mma<512>(ctx, a, tmap, threads, off, stream);
+    switch (levels) {
+        case 1: return launch_mma<1>(ctx, a, tmap, threads, smem_bytes, stream);
+        case 2: return launch_mma<2>(ctx, a, tmap, threads, smem_bytes, stream);
+        case 3: return launch_mma<3>(ctx, a, tmap, threads, smem_bytes, stream);
+        case 4: return launch_mma<4>(ctx, a, tmap, threads, smem_bytes, stream);
+        case 5: return launch_mma<5>(ctx, a, tmap, threads, smem_bytes, stream);
+    }
+    return VHR_ERR_INVALID;
 }
