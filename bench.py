@@ -212,6 +212,17 @@ def run_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    affinity = None
+    if args.affinity == "on" or (args.affinity == "auto" and world > 1):
+        # each rank on its own share of the host cores, before any pinned memory is allocated (first-touch locality
+        # of the clip it uploads in the e2e leg; tools/h2d_probe.py measures what this is worth on the box)
+        ncpu = os.cpu_count() or 1
+        per = max(1, ncpu // world)
+        try:
+            os.sched_setaffinity(0, set(range(local_rank * per, min(ncpu, (local_rank + 1) * per))))
+            affinity = f"cores {local_rank * per}-{min(ncpu, (local_rank + 1) * per) - 1} per rank"
+        except OSError:
+            affinity = None
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -402,7 +413,8 @@ def run_gpu(args):
                            "frames_per_step_per_gpu": T, "resident_clips_per_gpu": n_res,
                            "roi": "forehead + 2 cheeks, 36-vertex polygons (fused row masks)" if poly else "1 cheek rectangle",
                            "bpm": "whole-clip window, float32 detrend + FFT peak",
-                           "l2": "inputs (11.2 GB/clip at 1080p) larger than L2; no flush", "parallelism": f"clip-sharded x{world}"},
+                           "l2": "inputs (11.2 GB/clip at 1080p) larger than L2; no flush", "parallelism": f"clip-sharded x{world}",
+                           "host_affinity": affinity},
                 "roofline": {"bound": "hbm", "kernel": "collapse_sep_kernel", "achieved": achieved, "peak": peak_gbs,
                              "unit": "GB/s", "frac": achieved / peak_gbs,
                              "traffic": recorded_traffic("collapse_sep_kernel")[0] if args.workload == "c4" else None,
@@ -434,6 +446,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--affinity", default="off", choices=["off", "on", "auto"],
+                    help="pin each rank to its share of the host cores (auto: when N > 1)")
     ap.add_argument("--roi", default="rect", choices=["rect", "poly"], help="ROI stage: cheek rectangle, or forehead + cheek polygons")
     args = ap.parse_args()
     if args.impl == "reference":
