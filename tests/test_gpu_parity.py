@@ -538,6 +538,15 @@ def test_dropin_functions(vhr, eng):
         rppg.bandpass_fir(x[:50], 5.0, 0.7, 2)              # reference raises at 5 FPS (padlen 123)
     roi = rng.integers(0, 256, (25, 89, 3), dtype=np.uint8)
     assert rppg.get_avg(roi, 1) == float(np.mean(roi[:, :, 1]))
+    # what np.mean accepts beyond the scripts' uint8 ROIs: other dtypes / channel counts (float32 kernel, 1e-6)
+    rf = rng.standard_normal((17, 33, 4)) * 40 + 100
+    assert abs(rppg.get_avg(rf, 3) - float(np.mean(rf[:, :, 3]))) <= 1e-5 * 100
+    assert abs(rppg.get_avg(roi.astype(np.int16), 2) - float(np.mean(roi[:, :, 2]))) <= 1e-6 * 255
+    # (T, N) signals are filtered column by column, like sosfiltfilt / filtfilt along axis 0
+    X = np.stack([x, np.roll(x, 7) * 0.5, x[::-1]], 1)
+    for ours, ref in ((rppg.bandpass_butterworth(X, fps, 0.7, 2, 2), obpm.bandpass_butterworth(X, fps, 0.7, 2, 2)),
+                      (rppg.bandpass_fir(X, fps, 0.7, 2), obpm.bandpass_fir(X, fps, 0.7, 2))):
+        assert ours.shape == ref.shape == (300, 3) and rel_err(ours, ref) <= 1e-9
 
 
 def test_evm_roi_host_matches_device_path(vhr, eng):

@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) collapse_sep_kernel(const SepAr
     // ROIs that intersect this item (rectangle, or bounding box of a polygon)
     int rx1[KMAXF > 0 ? KMAXF : 1], ry1[KMAXF > 0 ? KMAXF : 1], rx2[KMAXF > 0 ? KMAXF : 1], ry2[KMAXF > 0 ? KMAXF : 1];
     bool hit[KMAXF > 0 ? KMAXF : 1];
+    uint32_t moff[KMAXF > 0 ? KMAXF : 1];        // RM == 2: word offset of this lane's mask column in row 0 of ROI k (host checks < 2^32)
     float acc[KMAXF > 0 ? KMAXF : 1][3];
     bool any_hit = false;
     if (KMAX > 0) {
@@ -152,6 +153,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) collapse_sep_kernel(const SepAr
                 rx1[k] = rc[0]; ry1[k] = rc[1]; rx2[k] = rc[2]; ry2[k] = rc[3];
                 hit[k] = rc[0] < xe && rc[2] > X0 && rc[1] < y1 && rc[3] > y0 && rc[2] > rc[0] && rc[3] > rc[1];
                 any_hit |= hit[k];
+                if (RM == 2) moff[k] = (uint32_t)(((size_t)t * a.Kstride + k) * a.H * a.MW + (X >> 5));
             }
         }
     }
@@ -354,7 +356,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) collapse_sep_kernel(const SepAr
                         // 4 mask bits of this lane's pixels (X % 4 == 0: they never straddle a word); only the
                         // words of the bounding box were written, lanes outside it do not read
                         if (X + 4 > rx1[k] && X < rx2[k]) {
-                            const uint32_t mw = __ldg(a.mask + (((size_t)t * a.Kstride + k) * a.H + y) * a.MW + (X >> 5));
+                            const uint32_t mw = __ldg(a.mask + (moff[k] + (uint32_t)y * (uint32_t)a.MW));
                             const uint32_t bits = (mw >> (X & 31)) & 0xFu;
 #pragma unroll
                             for (int px = 0; px < 4; ++px) {
@@ -578,6 +580,7 @@ int collapse_group(vhr_ctx* ctx, const float* d_level, const uint8_t* d_frames, 
         const size_t box_bytes = poly ? al(sizeof(int32_t) * 4 * (size_t)T * roi.K) : 0;
         const size_t cnt_bytes = poly ? al(sizeof(long long) * (size_t)T * roi.K) : 0;
         const size_t mask_bytes = poly ? al(sizeof(uint32_t) * (size_t)T * roi.K * H * MW) : 0;
+        VHR_REQUIRE(ctx, mask_bytes / 4 < 0xFFFFFFFFull, "polygon row masks exceed 2^32 words: split the clip along T");
         void* p = nullptr;
         int rc = vhr_scratch(ctx, part_bytes + box_bytes + cnt_bytes + mask_bytes, &p);
         if (rc != VHR_OK) return rc;

@@ -54,18 +54,26 @@ def get_roi_coords(bb_x1, bb_y1, bb_x2, bb_y2, horizontal_ratio, top_ratio, bott
 
 
 def get_avg(roi, color):
-    """rppg_VIDEO.py:60-66: np.mean(roi[:, :, color]) -- exact integer sum on the device."""
+    """rppg_VIDEO.py:60-66: np.mean(roi[:, :, color]).  uint8 ROIs (what the scripts pass): exact integer sum on
+    the device, one float64 division -- bit-identical to NumPy.  Any other dtype np.mean accepts goes through the
+    float32 masked-mean kernel (float64 accumulation of the float32-cast values)."""
     import torch
     eng = default_engine()
-    roi = np.ascontiguousarray(roi)
-    if roi.ndim != 3 or roi.shape[2] != 3 or roi.dtype != np.uint8:
-        raise ValueError("get_avg expects an (h, w, 3) uint8 ROI")
+    roi = np.asarray(roi)
+    if roi.ndim != 3 or not (0 <= color < roi.shape[2] or -roi.shape[2] <= color < 0):
+        raise IndexError("get_avg expects an (h, w, C) ROI and a channel index inside it")
     h, w = roi.shape[:2]
     if h == 0 or w == 0:
         return float("nan")
-    fr = torch.as_tensor(roi[None], device=eng.tdev)
-    m = eng.roi_mean_rect(fr, np.array([[[0, 0, w, h]]], dtype=np.int32))
-    return float(m[0, 0, color].item())
+    if roi.dtype == np.uint8 and roi.shape[2] == 3:
+        fr = torch.as_tensor(np.ascontiguousarray(roi)[None], device=eng.tdev)
+        m = eng.roi_mean_rect(fr, np.array([[[0, 0, w, h]]], dtype=np.int32))
+        return float(m[0, 0, color].item())
+    plane = np.ascontiguousarray(roi[:, :, color], dtype=np.float32)
+    fr = torch.as_tensor(np.repeat(plane[None, :, :, None], 3, axis=3), device=eng.tdev)
+    poly = np.array([[[[0, 0], [w - 1, 0], [w - 1, h - 1], [0, h - 1]]]], dtype=np.int32)
+    m, _ = eng.roi_mean_poly(fr, poly, np.array([[4]], dtype=np.int32))
+    return float(m[0, 0, 0].item())
 
 
 def process_frame(frame_bgr, landmarks):
@@ -88,20 +96,32 @@ def process_frame(frame_bgr, landmarks):
 def _one_window(signal):
     x = np.asarray(signal, dtype=np.float64)
     if x.ndim != 1:
-        raise ValueError("the device path filters one trace at a time (shape [T,])")
+        raise ValueError("the estimators take one trace at a time (shape [T,])")
     return x, np.zeros(1, dtype=np.int32), np.array([x.shape[0]], dtype=np.int32)
 
 
+def _windows_of(signal):
+    """(T,) -> one window; (T,N) -> N windows, one per column (the reference filters along axis 0)."""
+    x = np.asarray(signal, dtype=np.float64)
+    if x.ndim not in (1, 2):
+        raise ValueError("signal must be 1D (T,) or 2D (T, N) with time along axis 0")
+    cols = x[:, None] if x.ndim == 1 else x
+    T, N = cols.shape
+    flat = np.ascontiguousarray(cols.T).reshape(-1)
+    return x, flat, (np.arange(N, dtype=np.int32) * T).astype(np.int32), np.full(N, T, dtype=np.int32)
+
+
 def _filtfilt(signal, kind, coef, padlen):
-    x, st, ln = _one_window(signal)
+    x, flat, st, ln = _windows_of(signal)
     if x.shape[0] <= padlen:
         # scipy's message (signal/_signaltools.py:_validate_pad), raised by the reference at
         # rppg_VIDEO.py:404 for 5 FPS clips
         raise ValueError(f"The length of the input vector x must be greater than padlen, which is {padlen}.")
     eng = default_engine()
-    _, _, filt = eng.bpm_welch(x, st, ln, 1.0, (0.0, 1.0), detrend=DETREND_NONE, filt_kind=kind, coef=coef,
+    _, _, filt = eng.bpm_welch(flat, st, ln, 1.0, (0.0, 1.0), detrend=DETREND_NONE, filt_kind=kind, coef=coef,
                                want_filtered=True)
-    return filt[0].cpu().numpy()
+    out = filt.cpu().numpy()
+    return out[0] if x.ndim == 1 else np.ascontiguousarray(out.T)
 
 
 def _sos_padlen(sos):
