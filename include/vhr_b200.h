@@ -81,6 +81,14 @@ int vhr_pyr_dims(int W, int H, int levels, int32_t* w_out, int32_t* h_out);
  * one pass (levels 1..L-1 never touch HBM).  1 <= levels <= VHR_MAX_LEVELS. */
 int vhr_pyrdown_cascade(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int W,
                         int levels, float* d_level, void* stream);
+/* Diagnostics, host only: the tile plan the tensor-core kernel (csrc/pyrdown_umma.cu: 4 levels, W % 80 == 0) uses for a
+ * frame shape, so that tests can check its baked border weights on the CPU.  tiles: up to 12 x 8 int32 (first level-4
+ * row, level-4 rows, first level-3 row, rows, first level-2 row, rows, first input row, k-steps); codes: 12 x 17 (offset
+ * >> 4 of each k-step's weight slice in the blob, -1 past the end); wsp: 3 x 13 horizontal weights of level-2 pixels
+ * 0, 1, w2-1; meta: tiles, strips, border slices, blob bytes; blob (may be NULL): weight band + border slices in the
+ * UMMA K-major core-matrix layout.  VHR_ERR_UNSUPPORTED when the shape is not eligible. */
+int vhr_pyrdown_umma_plan(int H, int W, int32_t* tiles, int32_t* codes, int32_t* wsp, int32_t* meta,
+                          uint8_t* blob, int blob_cap);
 
 /* ---- EVM: temporal ideal bandpass (no reference code; spec = irfft(mask*rfft)) ----------
  * d_in/d_out float32 (T,P), time-major; keeps rfft bins with f_lo <= k*fps/T <= f_hi

@@ -37,6 +37,9 @@ struct vhr_ctx {
     void* sep_tab = nullptr;
     size_t sep_tab_bytes = 0;
     long long sep_key = -1;
+    // weight band + border slices of the tensor-core pyrDown (pyrdown_umma.cu), keyed by frame shape
+    void* umma_blob = nullptr;
+    long long umma_key = -1;
 };
 
 void vhr_set_error(vhr_ctx* ctx, const char* fmt, ...);
