@@ -83,7 +83,7 @@ int vhr_pyrdown_cascade(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int
                         int levels, float* d_level, void* stream);
 /* Diagnostics, host only: the tile plan the tensor-core kernel (csrc/pyrdown_umma.cu: 4 levels, W % 80 == 0) uses for a
  * frame shape, so that tests can check its baked border weights on the CPU.  tiles: up to 12 x 8 int32 (first level-4
- * row, level-4 rows, first level-3 row, rows, first level-2 row, rows, first input row, k-steps); codes: 12 x 17 (offset
+ * row, level-4 rows, first level-3 row, rows, first level-2 row, rows, first input row, k-steps); codes: 12 x 18 (offset
  * >> 4 of each k-step's weight slice in the blob, -1 past the end); wsp: 3 x 13 horizontal weights of level-2 pixels
  * 0, 1, w2-1; meta: tiles, strips, border slices, blob bytes; blob (may be NULL): weight band + border slices in the
  * UMMA K-major core-matrix layout.  VHR_ERR_UNSUPPORTED when the shape is not eligible. */

@@ -42,6 +42,21 @@ def down_matrix(n):
 
 
 def make_plan(H, W):
+    """The split with the fewest 64-row stages per frame (ties: the smaller tile height), as csrc/pyrdown_umma.cu."""
+    h4 = H
+    for _ in range(4):
+        h4 = (h4 + 1) // 2
+    ntiles = -(-h4 // MAX_N4)
+    best = None
+    for n4 in range(-(-h4 // ntiles), MAX_N4 + 1):
+        p = make_plan_n4(H, W, n4)
+        cost = sum(t["nks"] for t in p["tiles"])
+        if best is None or cost < best[0]:
+            best = (cost, p)
+    return best[1]
+
+
+def make_plan_n4(H, W, n4):
     assert W % 80 == 0
     h = [H]
     w = [W]
@@ -50,8 +65,7 @@ def make_plan(H, W):
         w.append((w[-1] + 1) // 2)
     c2v = down_matrix(h[1]) @ down_matrix(h[0])          # h2 x H, rows sum to 256
     c2h = down_matrix(w[1]) @ down_matrix(w[0])          # w2 x W
-    ntiles = -(-h[4] // MAX_N4)
-    n4 = -(-h[4] // ntiles)
+    ntiles = -(-h[4] // n4)
     tiles = []
     for t in range(ntiles):
         a = t * n4
@@ -65,7 +79,7 @@ def make_plan(H, W):
         nz = np.nonzero(c2v[r0:r1 + 1].sum(axis=0))[0]
         i0 = 4 * r0 - 8
         assert i0 <= nz[0]
-        nks = -(-(nz[-1] - i0 + 1) // 32)
+        nks = 2 * int(-(-(nz[-1] - i0 + 1) // 64))
         slices, codes = [], []
         for ks in range(nks):
             s = np.zeros((128, 32), dtype=np.int64)
@@ -78,7 +92,7 @@ def make_plan(H, W):
                     j = 32 * ks + k - 4 * m - 2
                     if 0 <= j <= 12:
                         gen[m, k] = W13[j]
-            codes.append("g" if np.array_equal(s, gen) else "s")
+            codes.append("g" if np.array_equal(s, gen) and ks <= 16 else "s")
             slices.append(s)
         tiles.append(dict(a=a, n4=n4t, g0=g0, n3=g1 - g0 + 1, r0=r0, nr=nr, i0=i0, nks=nks, slices=slices, codes=codes))
     # horizontal specials in window coordinates (L0 px 4x-6+j)

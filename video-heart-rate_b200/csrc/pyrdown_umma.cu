@@ -35,17 +35,21 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 #include <vector>
 
 namespace {
 
-constexpr int NSTAGE = 12;              // image stages of 32 rows x 256 bytes
-constexpr int STAGE_BYTES = 8192;
+#ifndef UMMA_NSTAGE
+#define UMMA_NSTAGE 6
+#endif
+constexpr int NSTAGE = UMMA_NSTAGE;     // image stages of 64 rows x 256 bytes = two k-steps
+constexpr int STAGE_BYTES = 16384;
 constexpr int PX = 20;                  // level-2 pixels per strip
 constexpr int NB = 12 * PX;             // fresh bytes per strip = MMA N
 constexpr int MAX_N4 = 29;              // level-4 rows per tile (4 n + 9 level-2 rows <= 128)
 constexpr int MAX_TILES = 12;
-constexpr int MAX_KS = 17;              // k-steps per tile (band offsets 0..16)
+constexpr int MAX_KS = 18;              // k-steps per tile, even (band offsets 0..16; a 17th / 18th step only ever meets unused rows)
 constexpr int MAX_SPECIAL = 8;
 constexpr int BAND_BYTES = 8192;
 constexpr int SLICE_BYTES = 4096;
@@ -70,7 +74,7 @@ struct UmmaTile {
     int a, n4;        // first level-4 row, rows
     int g0, n3;       // first level-3 row held by the tile, rows (<= 64)
     int r0, nr;       // first level-2 row, rows (<= 128)
-    int i0, nks;      // first input row fetched (may be negative), k-steps of 32 rows
+    int i0, nks;      // first input row fetched (may be negative), k-steps of 32 rows (even: a stage holds two)
 };
 
 struct UmmaArgs {
@@ -82,10 +86,11 @@ struct UmmaArgs {
     const uint8_t* blob;                  // band + special slices (global), blob_bytes
     int blob_bytes;
     UmmaTile tile[MAX_TILES];
-    unsigned short code[MAX_TILES][MAX_KS];   // byte offset >> 4 of the A slice inside the blob
+    alignas(4) unsigned short code[MAX_TILES][MAX_KS];   // byte offset >> 4 of the A slice inside the blob (read in pairs: one stage)
     int wsp[3][13];                       // horizontal weights of level-2 pixels 0, 1 and w2 - 1 (window coordinates)
     uint32_t* dbg;                        // optional: raw accumulators of (dbg_item, dbg_strip), 128 x 240
     int dbg_item, dbg_strip;
+    int mode;                             // measurement hook (VHR_UMMA_MODE): bit 0 = level-2 warps skip their arithmetic, bit 1 = no MMA is issued
 };
 
 // ---- PTX helpers ---------------------------------------------------------------------------
@@ -124,6 +129,11 @@ __device__ __forceinline__ void tma_box3d(uint32_t dst, const CUtensorMap* tmap,
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  :: "r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -152,9 +162,10 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 //   A: K-major, no swizzle: core matrix = 8 rows x 16 bytes (128 contiguous bytes); the two 16-byte K chunks of a
 //      k-step 128 bytes apart (leading), 8-row groups 256 bytes apart (stride).
 //   B: MN-major, SWIZZLE_128B: 128 bytes of N contiguous per K row (what a TMA box row is), 8-row groups 1024 bytes
-//      apart (stride), the second 128 bytes of N = the second box, 4096 bytes on (leading).
+//      apart (stride), the second 128 bytes of N = the second box, 8192 bytes on (leading); the second k-step of a
+//      stage starts 4096 bytes into each box.
 constexpr uint64_t A_DESC_HI = (uint64_t)((256u >> 4) | (1u << 14)) << 32 | (uint64_t)(128u >> 4) << 16;
-constexpr uint64_t B_DESC_HI = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32 | (uint64_t)(4096u >> 4) << 16;
+constexpr uint64_t B_DESC_HI = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32 | (uint64_t)(8192u >> 4) << 16;
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D = s32 (2 at [4,6)), A = B = unsigned 8 bit (0 at [7,10) and
 // [10,13)), A K-major (0 at 15), B MN-major (1 at 16), N >> 3 at [17,23), M >> 4 at [24,29).
 constexpr uint32_t IDESC = (2u << 4) | (1u << 16) | ((uint32_t)(NB >> 3) << 17) | ((128u >> 4) << 24);
@@ -230,7 +241,7 @@ __global__ void __launch_bounds__(THREADS, 1) pyrdown_umma_kernel(const __grid_c
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = smem_u32(smem);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;     // warp-uniform for the compiler
     const uint32_t bar0 = sbase + OFF_BAR;
     auto bar_full = [&](int s) { return bar0 + 8u * s; };
     auto bar_empty = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
@@ -269,52 +280,60 @@ __global__ void __launch_bounds__(THREADS, 1) pyrdown_umma_kernel(const __grid_c
     const int S = a.nstrips;
 
     if (warp == 0) {
-        // ---- TMA producer ----------------------------------------------------------------------------------------
-        if (lane == 0) {
-            asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap) : "memory");
-            uint32_t n = 0;
-            for (long long item = blockIdx.x; item < a.items; item += gridDim.x) {
-                const int f = (int)(item / a.ntiles);
-                const UmmaTile& tl = a.tile[(int)(item - (long long)f * a.ntiles)];
-                for (int s = 0; s < S; ++s) {
-                    for (int ks = 0; ks < tl.nks; ++ks, ++n) {
-                        const int st = n % NSTAGE;
-                        mbar_wait(bar_empty(st), ((n / NSTAGE) & 1) ^ 1);
-                        mbar_expect_tx(bar_full(st), STAGE_BYTES);
+        // ---- TMA producer: the whole warp runs the loop with warp-uniform values (operands stay in uniform registers),
+        // one elected lane issues.  One stage = 64 input rows x 256 bytes = two boxes.
+        if (lane == 0) asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap) : "memory");
+        uint32_t st = 0, ph = 0;
+        for (long long item = blockIdx.x; item < a.items; item += gridDim.x) {
+            const int f = (int)(item / a.ntiles);
+            const int t = (int)(item - (long long)f * a.ntiles);
+            const int i0 = a.tile[t].i0, nkp = a.tile[t].nks >> 1;
+            for (int s = 0; s < S; ++s) {
+                const int x = NB * s;
+                for (int kp = 0; kp < nkp; ++kp) {
+                    mbar_wait(bar_empty(st), ph ^ 1);
+                    if (elect_one()) {
                         const uint32_t dst = sbase + OFF_B + st * STAGE_BYTES;
-                        tma_box3d(dst, &tmap, NB * s, tl.i0 + 32 * ks, f, bar_full(st));
-                        tma_box3d(dst + 4096, &tmap, NB * s + 128, tl.i0 + 32 * ks, f, bar_full(st));
+                        mbar_expect_tx(bar_full(st), STAGE_BYTES);
+                        tma_box3d(dst, &tmap, x, i0 + 64 * kp, f, bar_full(st));
+                        tma_box3d(dst + 8192, &tmap, x + 128, i0 + 64 * kp, f, bar_full(st));
                     }
+                    __syncwarp();
+                    if (++st == NSTAGE) { st = 0; ph ^= 1; }
                 }
             }
         }
-        __syncwarp();
     } else if (warp == 1) {
-        // ---- MMA issuer ------------------------------------------------------------------------------------------
-        if (lane == 0) {
-            uint32_t n = 0, sc = 0;
-            for (long long item = blockIdx.x; item < a.items; item += gridDim.x) {
-                const int f = (int)(item / a.ntiles);
-                const int t = (int)(item - (long long)f * a.ntiles);
-                const int nks = a.tile[t].nks;
-                for (int s = 0; s < S; ++s, ++sc) {
-                    const int buf = sc & 1;
-                    mbar_wait(bar_tempty(buf), ((sc >> 1) & 1) ^ 1);
+        // ---- MMA issuer (same style): two MMAs (k-steps) per stage ------------------------------------------------------
+        uint32_t st = 0, ph = 0, sc = 0;
+        const uint32_t a_base = (sbase + OFF_A) >> 4, b_base = (sbase + OFF_B) >> 4;
+        for (long long item = blockIdx.x; item < a.items; item += gridDim.x) {
+            const int f = (int)(item / a.ntiles);
+            const int t = (int)(item - (long long)f * a.ntiles);
+            const int nkp = a.tile[t].nks >> 1;
+            const uint32_t* codes = reinterpret_cast<const uint32_t*>(&a.code[t][0]);
+            for (int s = 0; s < S; ++s, ++sc) {
+                const uint32_t buf = sc & 1;
+                mbar_wait(bar_tempty(buf), ((sc >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + 256u * buf;
+                for (int kp = 0; kp < nkp; ++kp) {
+                    const uint32_t cc = codes[kp];
+                    mbar_wait(bar_full(st), ph);
                     tc_fence_after();
-                    for (int ks = 0; ks < nks; ++ks, ++n) {
-                        const int st = n % NSTAGE;
-                        mbar_wait(bar_full(st), (n / NSTAGE) & 1);
-                        tc_fence_after();
-                        const uint64_t adesc = A_DESC_HI | (uint64_t)((((sbase + OFF_A) >> 4) + a.code[t][ks]) & 0x3FFFu);
-                        const uint64_t bdesc = B_DESC_HI | (uint64_t)(((sbase + OFF_B + st * STAGE_BYTES) >> 4) & 0x3FFFu);
-                        tc_mma_i8(tmem_base + 256u * buf, adesc, bdesc, IDESC, ks > 0);
-                        tc_commit(bar_empty(st));
+                    if (elect_one() && !(a.mode & 2)) {
+                        const uint32_t b0 = b_base + st * (STAGE_BYTES >> 4);
+                        tc_mma_i8(d_tmem, A_DESC_HI | (uint64_t)((a_base + (cc & 0xFFFFu)) & 0x3FFFu), B_DESC_HI | (uint64_t)(b0 & 0x3FFFu), IDESC, kp > 0);
+                        tc_mma_i8(d_tmem, A_DESC_HI | (uint64_t)((a_base + (cc >> 16)) & 0x3FFFu), B_DESC_HI | (uint64_t)((b0 + 256u) & 0x3FFFu), IDESC, 1u);
                     }
-                    tc_commit(bar_tfull(buf));
+                    if (elect_one()) tc_commit(bar_empty(st));
+                    __syncwarp();
+                    if (++st == NSTAGE) { st = 0; ph ^= 1; }
                 }
+                if (elect_one()) tc_commit(bar_tfull(buf));
+                __syncwarp();
             }
         }
-        __syncwarp();
     } else if (warp < 6) {
         // ---- level-2 warps: accumulators -> level 2 (13-tap) -> horizontal pass of level 3 ------------------------------
         const int q = warp & 3;
@@ -350,28 +369,28 @@ __global__ void __launch_bounds__(THREADS, 1) pyrdown_umma_kernel(const __grid_c
 #pragma unroll
                         for (int i = 0; i < 48; ++i) a.dbg[m * NB + i] = ca[i];
                     }
-                    l2_chunk<0>(a, prev, ca, p3, first, last, dst);
+                    if (!(a.mode & 1)) l2_chunk<0>(a, prev, ca, p3, first, last, dst);
                     tmem_wait_ld();
                     tmem_ld48(ta + 96, ca);
                     if (a.dbg && item == a.dbg_item && s == a.dbg_strip) {
 #pragma unroll
                         for (int i = 0; i < 48; ++i) a.dbg[m * NB + 48 + i] = cb[i];
                     }
-                    l2_chunk<1>(a, prev, cb, p3, first, last, dst);
+                    if (!(a.mode & 1)) l2_chunk<1>(a, prev, cb, p3, first, last, dst);
                     tmem_wait_ld();
                     tmem_ld48(ta + 144, cb);
                     if (a.dbg && item == a.dbg_item && s == a.dbg_strip) {
 #pragma unroll
                         for (int i = 0; i < 48; ++i) a.dbg[m * NB + 96 + i] = ca[i];
                     }
-                    l2_chunk<2>(a, prev, ca, p3, first, last, dst);
+                    if (!(a.mode & 1)) l2_chunk<2>(a, prev, ca, p3, first, last, dst);
                     tmem_wait_ld();
                     tmem_ld48(ta + 192, ca);
                     if (a.dbg && item == a.dbg_item && s == a.dbg_strip) {
 #pragma unroll
                         for (int i = 0; i < 48; ++i) a.dbg[m * NB + 144 + i] = cb[i];
                     }
-                    l2_chunk<3>(a, prev, cb, p3, first, last, dst);
+                    if (!(a.mode & 1)) l2_chunk<3>(a, prev, cb, p3, first, last, dst);
                     tmem_wait_ld();
                     tc_fence_before();
                     mbar_arrive(bar_tempty(buf));
@@ -379,7 +398,7 @@ __global__ void __launch_bounds__(THREADS, 1) pyrdown_umma_kernel(const __grid_c
 #pragma unroll
                         for (int i = 0; i < 48; ++i) a.dbg[m * NB + 192 + i] = ca[i];
                     }
-                    l2_chunk<4>(a, prev, ca, p3, first, last, dst);
+                    if (!(a.mode & 1)) l2_chunk<4>(a, prev, ca, p3, first, last, dst);
                 } else {
                     tc_fence_before();
                     mbar_arrive(bar_tempty(buf));
@@ -520,17 +539,16 @@ struct UmmaPlan {
 
 inline int canon(int m, int k) { return (m >> 3) * 256 + (k >> 4) * 128 + (m & 7) * 16 + (k & 15); }
 
-// VHR_OK, or VHR_ERR_UNSUPPORTED when the shape is not eligible
-int make_plan(int H, int W, UmmaPlan& p) {
-    if (W % 80 != 0 || W < 160 || H < 32 || W > 16384 || H > 16384) return VHR_ERR_UNSUPPORTED;
+// tiles of n4 level-4 rows (the last one takes the rest); VHR_OK, or VHR_ERR_UNSUPPORTED when the shape is not eligible
+int make_plan_n4(int H, int W, int n4, UmmaPlan& p) {
+    if (W % 80 != 0 || W < 160 || H < 64 || W > 16384 || H > 16384) return VHR_ERR_UNSUPPORTED;
     p.H = H; p.W = W;
     p.h[0] = H; p.w[0] = W;
     for (int l = 1; l <= 4; ++l) { p.h[l] = (p.h[l - 1] + 1) / 2; p.w[l] = (p.w[l - 1] + 1) / 2; }
     if (p.h[3] < 3 || p.w[3] < 3) return VHR_ERR_UNSUPPORTED;
-    p.ntiles = (p.h[4] + MAX_N4 - 1) / MAX_N4;
-    if (p.ntiles > MAX_TILES) return VHR_ERR_UNSUPPORTED;
+    p.ntiles = (p.h[4] + n4 - 1) / n4;
+    if (p.ntiles > MAX_TILES || n4 > MAX_N4) return VHR_ERR_UNSUPPORTED;
     p.nstrips = p.w[2] / PX + 1;
-    const int n4 = (p.h[4] + p.ntiles - 1) / p.ntiles;
     p.blob.assign(BAND_BYTES, 0);
     for (int q = -128; q < 128; ++q)
         for (int k = 0; k < 32; ++k) {
@@ -562,8 +580,8 @@ int make_plan(int H, int W, UmmaPlan& p) {
             }
             if (rows[m].lo < -100000 || sum != 256) return VHR_ERR_UNSUPPORTED;
         }
-        tl.nks = (hi - tl.i0 + 1 + 31) / 32;
-        if (tl.nks > MAX_KS || tl.nks < 1) return VHR_ERR_UNSUPPORTED;
+        tl.nks = 2 * ((hi - tl.i0 + 1 + 63) / 64);           // whole stages of 64 rows; a trailing k-step carries zero weights
+        if (tl.nks > MAX_KS || tl.nks < 2) return VHR_ERR_UNSUPPORTED;
         for (int ks = 0; ks < tl.nks; ++ks) {
             bool generic = true;
             uint8_t sl[SLICE_BYTES];
@@ -578,7 +596,7 @@ int make_plan(int H, int W, UmmaPlan& p) {
                     if (wv != gv) generic = false;
                     sl[canon(m, k)] = (uint8_t)wv;
                 }
-            if (generic) {
+            if (generic && ks <= 16) {
                 p.code[t][ks] = (unsigned short)(((16 - ks) * 256) >> 4);
             } else {
                 int found = -1;
@@ -615,10 +633,27 @@ int make_plan(int H, int W, UmmaPlan& p) {
     return VHR_OK;
 }
 
+// The split with the fewest 64-row stages per frame (ties: the smaller tile height).
+int make_plan(int H, int W, UmmaPlan& best) {
+    if (H < 32) return VHR_ERR_UNSUPPORTED;
+    const int h4 = (((((H + 1) / 2 + 1) / 2 + 1) / 2) + 1) / 2;
+    const int ntiles = (h4 + MAX_N4 - 1) / MAX_N4;
+    int best_cost = 1 << 30, rc_any = VHR_ERR_UNSUPPORTED;
+    for (int n4 = (h4 + ntiles - 1) / ntiles; n4 <= MAX_N4; ++n4) {
+        UmmaPlan p;
+        const int rc = make_plan_n4(H, W, n4, p);
+        if (rc != VHR_OK) continue;
+        int cost = 0;
+        for (int t = 0; t < p.ntiles; ++t) cost += p.tile[t].nks;
+        if (cost < best_cost) { best_cost = cost; best = p; rc_any = VHR_OK; }
+    }
+    return rc_any;
+}
+
 }  // namespace
 
 // Diagnostics (tests): the tile plan of a frame shape.  tiles: ntiles x 8 int32 (a, n4, g0, n3, r0, nr, i0, nks); codes:
-// ntiles x 17 (A-slice offset >> 4 inside the blob); wsp: 3 x 13; meta: ntiles, nstrips, nspecial, blob bytes.
+// ntiles x 18 (A-slice offset >> 4 inside the blob); wsp: 3 x 13; meta: ntiles, nstrips, nspecial, blob bytes.
 // blob may be NULL.  Host only.
 extern "C" int vhr_pyrdown_umma_plan(int H, int W, int32_t* tiles, int32_t* codes, int32_t* wsp, int32_t* meta, uint8_t* blob,
                                      int blob_cap) {
@@ -674,7 +709,7 @@ int vhr_pyrdown_umma(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int W,
     CUtensorMap tmap;
     const cuuint64_t gdim[3] = {(cuuint64_t)W * 3, (cuuint64_t)H, (cuuint64_t)T};
     const cuuint64_t gstr[2] = {(cuuint64_t)W * 3, (cuuint64_t)W * 3 * (cuuint64_t)H};
-    const cuuint32_t box[3] = {128, 32, 1};
+    const cuuint32_t box[3] = {128, 64, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     if (encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(d_frames), gdim, gstr, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -699,6 +734,8 @@ int vhr_pyrdown_umma(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int W,
         unsigned long long ptr = 0; int it = 0, st = 0;
         if (sscanf(dbg, "%llu,%d,%d", &ptr, &it, &st) == 3) { a.dbg = reinterpret_cast<uint32_t*>(ptr); a.dbg_item = it; a.dbg_strip = st; }
     }
+    const char* mode = getenv("VHR_UMMA_MODE");
+    a.mode = mode ? atoi(mode) : 0;
     VHR_CHECK_CUDA(ctx, cudaFuncSetAttribute(pyrdown_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     long long grid = ctx->num_sms;
     if (grid > a.items) grid = a.items;
