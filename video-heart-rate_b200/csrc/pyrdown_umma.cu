@@ -150,7 +150,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* d) {
                    "=r"(d[8]), "=r"(d[9]), "=r"(d[10]), "=r"(d[11]), "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15])
                  : "r"(taddr));
 }
-__device__ __forceinline__ void tmem_ld48(uint32_t taddr, uint32_t (&d)[48]) {
+__device__ __forceinline__ void tmem_ld48(uint32_t taddr, uint32_t* d) {
     tmem_ld16(taddr, d);
     tmem_ld16(taddr + 16, d + 16);
     tmem_ld16(taddr + 32, d + 32);
@@ -176,16 +176,18 @@ __device__ __forceinline__ int refl101(int i, int n) {
     return i < 0 ? -i : i;
 }
 
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+
 // ---- level-2 warps: one chunk of 48 accumulator columns = 4 level-2 pixels = 2 level-3 pixels of the row ------------
-template <int C>
-__device__ __forceinline__ void l2_chunk(const UmmaArgs& a, uint32_t (&prev)[30], const uint32_t (&cur)[48], float (&p3)[3][3],
-                                         const bool first, const bool last, float* __restrict__ dst) {
-    uint32_t v[78];
-#pragma unroll
-    for (int i = 0; i < 30; ++i) v[i] = prev[i];
-#pragma unroll
-    for (int i = 0; i < 48; ++i) v[30 + i] = cur[i];
-    float l2[4][3];
+// One code instance for the five chunks of a strip (the unrolled form, 19 KB per strip, starved on instruction fetch:
+// 66 % of the level-2 warps' samples were no_instruction, profiles/r2_ncu_v_pyrdown_umma_v2.txt).
+// v = 30 carried columns + the 48 of this chunk; level-2 slot e of the chunk sits at v[12 e + 3 j + ch], j = 0..12.
+__device__ __forceinline__ void l2_values(const uint32_t (&v)[78], float (&l2)[4][3]) {
 #pragma unroll
     for (int el = 0; el < 4; ++el) {
 #pragma unroll
@@ -197,46 +199,37 @@ __device__ __forceinline__ void l2_chunk(const UmmaArgs& a, uint32_t (&prev)[30]
             l2[el][ch] = __uint2float_rn(acc);
         }
     }
-    if (C == 0) {
-        // frame borders: level-2 pixels 0, 1 (slots 1, 2 of the first strip) and w2 - 1 (slot 0 of the flush strip) carry
-        // reflect-101 folded into their weights; the virtual pixels -1, -2 and w2 mirror their neighbours
-        if (first) {
+}
+// frame borders (first chunk of the first / of the flush strip only): level-2 pixels 0, 1 (slots 1, 2 of the first strip)
+// and w2 - 1 (slot 0 of the flush strip) carry reflect-101 folded into their weights; the virtual pixels -1, -2 and w2
+// mirror their neighbours
+__device__ __forceinline__ void l2_borders(const UmmaArgs& a, const uint32_t (&v)[78], float (&l2)[4][3], float (&p3)[3][3], const bool first) {
+    if (first) {
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-#pragma unroll
-                for (int ch = 0; ch < 3; ++ch) {
-                    uint32_t acc = 0;
-#pragma unroll
-                    for (int j = 0; j < 13; ++j) acc += (uint32_t)a.wsp[k][j] * v[12 * (k + 1) + 3 * j + ch];
-                    l2[k + 1][ch] = __uint2float_rn(acc);
-                }
-            }
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) { l2[0][ch] = l2[2][ch]; p3[2][ch] = l2[3][ch]; }
-        }
-        if (last) {
+        for (int k = 0; k < 2; ++k) {
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
                 uint32_t acc = 0;
 #pragma unroll
-                for (int j = 0; j < 13; ++j) acc += (uint32_t)a.wsp[2][j] * v[3 * j + ch];
-                l2[0][ch] = __uint2float_rn(acc);
-                l2[1][ch] = p3[2][ch];
+                for (int j = 0; j < 13; ++j) acc += (uint32_t)a.wsp[k][j] * v[12 * (k + 1) + 3 * j + ch];
+                l2[k + 1][ch] = __uint2float_rn(acc);
             }
         }
-    }
-    // horizontal pass of level 3: pixels 2C and 2C+1 of the strip from level-2 slots 4C-3 .. 4C+3
 #pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-        const float e0 = p3[0][ch], e1 = p3[1][ch], e2 = p3[2][ch], e3 = l2[0][ch], e4 = l2[1][ch], e5 = l2[2][ch], e6 = l2[3][ch];
-        dst[((2 * C) * 3 + ch) * L3H_PITCH] = (e0 + e4) + 4.0f * (e1 + e3) + 6.0f * e2;
-        dst[((2 * C + 1) * 3 + ch) * L3H_PITCH] = (e2 + e6) + 4.0f * (e3 + e5) + 6.0f * e4;
-        p3[0][ch] = e4; p3[1][ch] = e5; p3[2][ch] = e6;
-    }
+        for (int ch = 0; ch < 3; ++ch) { l2[0][ch] = l2[2][ch]; p3[2][ch] = l2[3][ch]; }
+    } else {
 #pragma unroll
-    for (int i = 0; i < 30; ++i) prev[i] = v[48 + i];
+        for (int ch = 0; ch < 3; ++ch) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int j = 0; j < 13; ++j) acc += (uint32_t)a.wsp[2][j] * v[3 * j + ch];
+            l2[0][ch] = __uint2float_rn(acc);
+            l2[1][ch] = p3[2][ch];
+        }
+    }
 }
 
+template <bool DBG>
 __global__ void __launch_bounds__(THREADS, 1) pyrdown_umma_kernel(const __grid_constant__ UmmaArgs a, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -339,66 +332,60 @@ __global__ void __launch_bounds__(THREADS, 1) pyrdown_umma_kernel(const __grid_c
         const int q = warp & 3;
         const int m = 32 * q + lane;
         const uint32_t tlane = tmem_base + ((uint32_t)(32 * q) << 16);
-        const int ridx = (m & 1) * L3H_ODD + (m >> 1);
+        const uint32_t ridx = 4u * ((m & 1) * L3H_ODD + (m >> 1));
         uint32_t sc = 0;
         for (long long item = blockIdx.x; item < a.items; item += gridDim.x) {
             const int f = (int)(item / a.ntiles);
             const int t = (int)(item - (long long)f * a.ntiles);
             const bool active = 32 * q < a.tile[t].nr;
-            uint32_t prev[30];
-            float p3[3][3];
+            uint32_t v[78];                      // [0, 30): columns carried from the previous chunk, [30, 78): this chunk
+            float p3[3][3];                      // the three level-2 pixels before this chunk
 #pragma unroll
-            for (int i = 0; i < 30; ++i) prev[i] = 0;
+            for (int i = 0; i < 78; ++i) v[i] = 0;
 #pragma unroll
             for (int i = 0; i < 3; ++i) { p3[i][0] = 0.f; p3[i][1] = 0.f; p3[i][2] = 0.f; }
             for (int s = 0; s < S; ++s, ++sc) {
                 const int buf = sc & 1;
                 const uint32_t ph = (sc >> 1) & 1;
-                float* dst = reinterpret_cast<float*>(smem + OFF_L3H) + buf * (L3H_COLS * L3H_PITCH) + ridx;
+                uint32_t dst = sbase + OFF_L3H + buf * (L3H_COLS * L3H_PITCH * 4) + ridx;
                 mbar_wait(bar_l3empty(buf), ph ^ 1);
                 mbar_wait(bar_tfull(buf), ph);
                 tc_fence_after();
                 if (active) {
-                    const uint32_t ta = tlane + 256u * buf;
-                    const bool first = s == 0, last = s == S - 1;
-                    uint32_t ca[48], cb[48];
-                    tmem_ld48(ta, ca);
-                    tmem_wait_ld();
-                    tmem_ld48(ta + 48, cb);
-                    if (a.dbg && item == a.dbg_item && s == a.dbg_strip) {
+                    uint32_t ta = tlane + 256u * buf;
+                    const bool border = s == 0 || s == S - 1;
+                    tmem_ld48(ta, v + 30);
+#pragma unroll 1
+                    for (int c = 0; c < 5; ++c) {
+                        tmem_wait_ld();
+                        if (DBG) {
+                            if (a.dbg && item == a.dbg_item && s == a.dbg_strip) {
 #pragma unroll
-                        for (int i = 0; i < 48; ++i) a.dbg[m * NB + i] = ca[i];
-                    }
-                    if (!(a.mode & 1)) l2_chunk<0>(a, prev, ca, p3, first, last, dst);
-                    tmem_wait_ld();
-                    tmem_ld48(ta + 96, ca);
-                    if (a.dbg && item == a.dbg_item && s == a.dbg_strip) {
+                                for (int i = 0; i < 48; ++i) a.dbg[m * NB + 48 * c + i] = v[30 + i];
+                            }
+                        }
+                        float l2[4][3];
+                        if (!(a.mode & 1)) l2_values(v, l2);
+                        if (c == 0 && border) l2_borders(a, v, l2, p3, s == 0);
 #pragma unroll
-                        for (int i = 0; i < 48; ++i) a.dbg[m * NB + 48 + i] = cb[i];
-                    }
-                    if (!(a.mode & 1)) l2_chunk<1>(a, prev, cb, p3, first, last, dst);
-                    tmem_wait_ld();
-                    tmem_ld48(ta + 144, cb);
-                    if (a.dbg && item == a.dbg_item && s == a.dbg_strip) {
+                        for (int i = 0; i < 30; ++i) v[i] = v[48 + i];
+                        ta += 48;
+                        if (c < 4) {
+                            tmem_ld48(ta, v + 30);
+                        } else {
+                            tc_fence_before();
+                            mbar_arrive(bar_tempty(buf));
+                        }
+                        // horizontal pass of level 3: pixels 2c and 2c+1 of the strip from level-2 slots 4c-3 .. 4c+3
 #pragma unroll
-                        for (int i = 0; i < 48; ++i) a.dbg[m * NB + 96 + i] = ca[i];
+                        for (int ch = 0; ch < 3; ++ch) {
+                            const float e0 = p3[0][ch], e1 = p3[1][ch], e2 = p3[2][ch], e3 = l2[0][ch], e4 = l2[1][ch], e5 = l2[2][ch], e6 = l2[3][ch];
+                            sts_f32(dst + ch * (L3H_PITCH * 4), (e0 + e4) + 4.0f * (e1 + e3) + 6.0f * e2);
+                            sts_f32(dst + (3 + ch) * (L3H_PITCH * 4), (e2 + e6) + 4.0f * (e3 + e5) + 6.0f * e4);
+                            p3[0][ch] = e4; p3[1][ch] = e5; p3[2][ch] = e6;
+                        }
+                        dst += 6 * L3H_PITCH * 4;
                     }
-                    if (!(a.mode & 1)) l2_chunk<2>(a, prev, ca, p3, first, last, dst);
-                    tmem_wait_ld();
-                    tmem_ld48(ta + 192, ca);
-                    if (a.dbg && item == a.dbg_item && s == a.dbg_strip) {
-#pragma unroll
-                        for (int i = 0; i < 48; ++i) a.dbg[m * NB + 144 + i] = cb[i];
-                    }
-                    if (!(a.mode & 1)) l2_chunk<3>(a, prev, cb, p3, first, last, dst);
-                    tmem_wait_ld();
-                    tc_fence_before();
-                    mbar_arrive(bar_tempty(buf));
-                    if (a.dbg && item == a.dbg_item && s == a.dbg_strip) {
-#pragma unroll
-                        for (int i = 0; i < 48; ++i) a.dbg[m * NB + 192 + i] = ca[i];
-                    }
-                    if (!(a.mode & 1)) l2_chunk<4>(a, prev, ca, p3, first, last, dst);
                 } else {
                     tc_fence_before();
                     mbar_arrive(bar_tempty(buf));
@@ -409,7 +396,7 @@ __global__ void __launch_bounds__(THREADS, 1) pyrdown_umma_kernel(const __grid_c
     } else if (warp < 8) {
         // ---- level-3 warps: vertical pass of level 3, horizontal pass of level 4 ------------------------------------------
         const int i = (warp - 6) * 32 + lane;
-        const int widx = (i & 1) * L4H_ODD + (i >> 1);
+        const uint32_t widx = 4u * ((i & 1) * L4H_ODD + (i >> 1));
         uint32_t sc = 0;
         for (long long item = blockIdx.x; item < a.items; item += gridDim.x) {
             const int f = (int)(item / a.ntiles);
@@ -419,7 +406,7 @@ __global__ void __launch_bounds__(THREADS, 1) pyrdown_umma_kernel(const __grid_c
 #pragma unroll
             for (int d = 0; d < 5; ++d) {
                 const int r = refl101(2 * g - 2 + d, a.h2) - tl.r0;
-                idx[d] = (r & 1) * L3H_ODD + (r >> 1);
+                idx[d] = 4 * ((r & 1) * L3H_ODD + (r >> 1));
             }
             float c3[3][3];
 #pragma unroll
@@ -427,15 +414,16 @@ __global__ void __launch_bounds__(THREADS, 1) pyrdown_umma_kernel(const __grid_c
             for (int s = 0; s < S; ++s, ++sc) {
                 const int buf = sc & 1;
                 const uint32_t ph = (sc >> 1) & 1;
-                const float* src = reinterpret_cast<const float*>(smem + OFF_L3H) + buf * (L3H_COLS * L3H_PITCH);
+                const uint32_t src = sbase + OFF_L3H + buf * (L3H_COLS * L3H_PITCH * 4);
                 mbar_wait(bar_l3full(buf), ph);
                 float l3[13][3];                    // slots -3 .. 9
 #pragma unroll
                 for (int e = 0; e < 10; ++e) {
 #pragma unroll
                     for (int ch = 0; ch < 3; ++ch) {
-                        const float* p = src + (e * 3 + ch) * L3H_PITCH;
-                        l3[e + 3][ch] = (p[idx[0]] + p[idx[4]]) + 4.0f * (p[idx[1]] + p[idx[3]]) + 6.0f * p[idx[2]];
+                        const uint32_t p = src + (e * 3 + ch) * (L3H_PITCH * 4);
+                        l3[e + 3][ch] = (lds_f32(p + idx[0]) + lds_f32(p + idx[4])) + 4.0f * (lds_f32(p + idx[1]) + lds_f32(p + idx[3])) +
+                                        6.0f * lds_f32(p + idx[2]);
                     }
                 }
                 mbar_arrive(bar_l3empty(buf));
@@ -445,14 +433,14 @@ __global__ void __launch_bounds__(THREADS, 1) pyrdown_umma_kernel(const __grid_c
                     if (s == S - 1) l3[4][ch] = c3[2][ch];
                     l3[0][ch] = c3[0][ch]; l3[1][ch] = c3[1][ch]; l3[2][ch] = c3[2][ch];
                 }
-                float* dst = reinterpret_cast<float*>(smem + OFF_L4H) + buf * (L4H_COLS * L4H_PITCH) + widx;
+                const uint32_t dst = sbase + OFF_L4H + buf * (L4H_COLS * L4H_PITCH * 4) + widx;
                 mbar_wait(bar_l4empty(buf), ph ^ 1);
 #pragma unroll
                 for (int e = 0; e < 5; ++e) {
 #pragma unroll
                     for (int ch = 0; ch < 3; ++ch)
-                        dst[(e * 3 + ch) * L4H_PITCH] = (l3[2 * e][ch] + l3[2 * e + 4][ch]) + 4.0f * (l3[2 * e + 1][ch] + l3[2 * e + 3][ch]) +
-                                                        6.0f * l3[2 * e + 2][ch];
+                        sts_f32(dst + (e * 3 + ch) * (L4H_PITCH * 4),
+                                (l3[2 * e][ch] + l3[2 * e + 4][ch]) + 4.0f * (l3[2 * e + 1][ch] + l3[2 * e + 3][ch]) + 6.0f * l3[2 * e + 2][ch]);
                 }
                 mbar_arrive(bar_l4full(buf));
 #pragma unroll
@@ -471,19 +459,20 @@ __global__ void __launch_bounds__(THREADS, 1) pyrdown_umma_kernel(const __grid_c
 #pragma unroll
             for (int d = 0; d < 5; ++d) {
                 const int r = refl101(2 * r4 - 2 + d, a.h3) - tl.g0;
-                idx[d] = (r & 1) * L4H_ODD + (r >> 1);
+                idx[d] = 4 * ((r & 1) * L4H_ODD + (r >> 1));
             }
             float* orow = a.out + ((size_t)f * a.h4 + r4) * (size_t)a.w4 * 3;
             for (int s = 0; s < S; ++s, ++sc) {
                 const int buf = sc & 1;
                 const uint32_t ph = (sc >> 1) & 1;
-                const float* src = reinterpret_cast<const float*>(smem + OFF_L4H) + buf * (L4H_COLS * L4H_PITCH);
+                const uint32_t src = sbase + OFF_L4H + buf * (L4H_COLS * L4H_PITCH * 4);
                 mbar_wait(bar_l4full(buf), ph);
                 float o[15];
 #pragma unroll
                 for (int c = 0; c < 15; ++c) {
-                    const float* p = src + c * L4H_PITCH;
-                    o[c] = ((p[idx[0]] + p[idx[4]]) + 4.0f * (p[idx[1]] + p[idx[3]]) + 6.0f * p[idx[2]]) * 2.3283064365386963e-10f;   // 2^-32
+                    const uint32_t p = src + c * (L4H_PITCH * 4);
+                    o[c] = ((lds_f32(p + idx[0]) + lds_f32(p + idx[4])) + 4.0f * (lds_f32(p + idx[1]) + lds_f32(p + idx[3])) +
+                            6.0f * lds_f32(p + idx[2])) * 2.3283064365386963e-10f;   // 2^-32
                 }
                 mbar_arrive(bar_l4empty(buf));
                 if (valid) {
@@ -736,9 +725,10 @@ int vhr_pyrdown_umma(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int W,
     }
     const char* mode = getenv("VHR_UMMA_MODE");
     a.mode = mode ? atoi(mode) : 0;
-    VHR_CHECK_CUDA(ctx, cudaFuncSetAttribute(pyrdown_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    auto kern = a.dbg ? pyrdown_umma_kernel<true> : pyrdown_umma_kernel<false>;
+    VHR_CHECK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     long long grid = ctx->num_sms;
     if (grid > a.items) grid = a.items;
-    pyrdown_umma_kernel<<<(int)grid, THREADS, SMEM_BYTES, stream>>>(a, tmap);
+    kern<<<(int)grid, THREADS, SMEM_BYTES, stream>>>(a, tmap);
     return vhr_after_launch(ctx, "pyrdown_umma_kernel");
 }
