@@ -116,7 +116,7 @@ def test_pyrdown_streaming_kernels(vhr, eng, case, monkeypatch):
     sel = np.r_[0:n_ref // 2, T - (n_ref - n_ref // 2):T]
     ref = oevm.pyrdown_cascade(fr[sel], levels)
     outs = {}
-    for impl in ("stream", "mma"):
+    for impl in ("stream", "mma"):                            # (the tcgen05 kernel has its own test below)
         monkeypatch.setenv("VHR_PYRDOWN_IMPL", impl)
         got = eng.pyrdown(frd, levels).cpu().numpy()
         monkeypatch.delenv("VHR_PYRDOWN_IMPL")
@@ -130,6 +130,51 @@ def test_pyrdown_streaming_kernels(vhr, eng, case, monkeypatch):
         np.testing.assert_array_equal(outs["stream"], outs["mma"])
     else:
         assert rel_err(outs["stream"], outs["mma"]) <= 1e-6   # every frame, every share boundary
+
+
+@pytest.mark.parametrize("case", [(5, 1080, 1920), (4, 720, 1280), (7, 480, 640), (300, 67, 1280), (9, 1081, 160), (3, 2160, 320),
+                                  (400, 90, 720), (2, 1079, 160), (160, 64, 160), (3, 135, 240), (2, 1440, 2560)])
+def test_pyrdown_tensor_core_kernel(vhr, eng, case, monkeypatch):
+    """csrc/pyrdown_umma.cu (tcgen05.mma kind::i8 vertical composite, TMEM accumulators; the default for 4 levels and
+    W % 80 == 0) against the oracle on the first and last frames and against the streaming kernel on every frame: several
+    row tiles, a single tile, odd heights at every level, more items than CTAs, widths from 2 to 32 strips."""
+    import torch
+    T, H, W = case
+    rng = np.random.default_rng(T + H + W)
+    fr = rng.integers(0, 256, (T, H, W, 3), dtype=np.uint8)
+    frd = torch.as_tensor(fr, device=eng.tdev)
+    before = eng.launch_count()
+    monkeypatch.setenv("VHR_PYRDOWN_IMPL", "umma")
+    got = eng.pyrdown(frd, 4).cpu().numpy()
+    assert eng.launch_count() == before + 1
+    monkeypatch.setenv("VHR_PYRDOWN_IMPL", "stream" if W % 64 == 0 else "mma")
+    other = eng.pyrdown(frd, 4).cpu().numpy()
+    monkeypatch.delenv("VHR_PYRDOWN_IMPL")
+    n_ref = min(T, 4)
+    sel = np.r_[0:n_ref // 2, T - (n_ref - n_ref // 2):T]
+    assert rel_err(got[sel], oevm.pyrdown_cascade(fr[sel], 4)) <= 2e-6      # measured 2e-7 (float32 levels 3-4); the contract is REL
+    assert rel_err(got, other) <= 2e-6
+    # the kernel is a pure function of the frame: frames repeated at other positions of the clip (other CTAs, other
+    # accumulator buffers, other pipeline phases) give the same bits
+    if T >= 4:
+        fr2 = np.concatenate([fr[-2:], fr[:-2]])
+        got2 = eng.pyrdown(torch.as_tensor(fr2, device=eng.tdev), 4).cpu().numpy()
+        np.testing.assert_array_equal(got2, np.concatenate([got[-2:], got[:-2]]))
+
+
+def test_pyrdown_tensor_core_kernel_constant_and_extremes(vhr, eng):
+    """All-255 frames exercise the largest accumulators (255 * 256 per column, 255 * 65536 per level-2 value): every level
+    of a constant image is that constant, exactly; a single bright pixel checks every weight of the composite filters."""
+    import torch
+    fr = np.full((2, 256, 320, 3), 255, dtype=np.uint8)
+    got = eng.pyrdown(torch.as_tensor(fr, device=eng.tdev), 4).cpu().numpy()
+    np.testing.assert_array_equal(got, np.full_like(got, 255.0))
+    fr = np.zeros((6, 256, 320, 3), dtype=np.uint8)
+    for k, (y, x) in enumerate([(0, 0), (255, 319), (128, 7), (31, 160), (100, 239), (1, 318)]):
+        fr[k, y, x, k % 3] = 255
+    got = eng.pyrdown(torch.as_tensor(fr, device=eng.tdev), 4).cpu().numpy()
+    ref = oevm.pyrdown_cascade(fr, 4)
+    np.testing.assert_allclose(got, ref, rtol=2e-6, atol=1e-9)
 
 
 # --------------------------------------------------------------------------------- bandpass

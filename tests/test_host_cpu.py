@@ -181,3 +181,48 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["value"] > 0 and line["vs_baseline"] is None
+
+
+@pytest.mark.parametrize("hw", [(1080, 1920), (720, 1280), (480, 640), (67, 1280), (1081, 160), (2160, 320), (90, 720), (64, 160)])
+def test_tensor_core_pyrdown_plan_matches_the_emulation(pkg, hw):
+    """csrc/pyrdown_umma.cu bakes cv2's reflect-101 borders into weight slices on the host.  The plan it builds for a
+    frame shape (vhr_pyrdown_umma_plan: tiles, per-k-step slices read back through the same descriptor offsets the MMA
+    uses, border weights of the horizontal pass) equals the one of tools/probes/umma_emulate.py, and that emulation of
+    the kernel's data flow (tiles, lagged strips, register carries, border patches) reproduces the oracle exactly."""
+    if not os.path.exists(pkg.LIB_PATH):
+        pytest.skip("libvhr_b200.so not built (run python __graft_entry__.py)")
+    sys.path.insert(0, os.path.join(ROOT, "tools", "probes"))
+    import umma_emulate as em
+    from oracle import evm as oevm
+    H, W = hw
+    lib = ctypes.CDLL(pkg.LIB_PATH)
+    tiles = np.zeros((12, 8), np.int32)
+    codes = np.zeros((12, 18), np.int32)
+    wsp = np.zeros((3, 13), np.int32)
+    meta = np.zeros(4, np.int32)
+    blob = np.zeros(8192 + 8 * 4096, np.uint8)
+    vp = ctypes.c_void_p
+    lib.vhr_pyrdown_umma_plan.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, ctypes.c_int]
+    assert lib.vhr_pyrdown_umma_plan(H, W, tiles.ctypes.data, codes.ctypes.data, wsp.ctypes.data, meta.ctypes.data,
+                                     blob.ctypes.data, blob.size) == 0
+    plan = em.make_plan(H, W)
+    assert meta[0] == len(plan["tiles"]) and meta[1] == plan["nstrips"]
+
+    def canon(m, k):                      # UMMA K-major core-matrix layout, no swizzle
+        return (m >> 3) * 256 + (k >> 4) * 128 + (m & 7) * 16 + (k & 15)
+
+    mm, kk = np.meshgrid(np.arange(128), np.arange(32), indexing="ij")
+    for t, tl in enumerate(plan["tiles"]):
+        assert list(tiles[t]) == [tl[k] for k in ("a", "n4", "g0", "n3", "r0", "nr", "i0", "nks")]
+        assert tl["nks"] % 2 == 0
+        for ks in range(tl["nks"]):
+            sl = blob[codes[t, ks] * 16 + canon(mm, kk)]
+            np.testing.assert_array_equal(sl[:tl["nr"]], tl["slices"][ks][:tl["nr"]])
+    w2 = plan["w"][2]
+    for k, x in enumerate((0, 1, w2 - 1)):
+        np.testing.assert_array_equal(wsp[k], plan["special"][x])
+    if H * W <= 720 * 1280:
+        fr = np.random.default_rng(H + W).integers(0, 256, (H, W, 3), dtype=np.uint8)
+        np.testing.assert_array_equal(em.emulate(fr, plan), oevm.pyrdown_cascade(fr[None], 4)[0])
+    assert lib.vhr_pyrdown_umma_plan(1080, 1000, tiles.ctypes.data, codes.ctypes.data, wsp.ctypes.data, meta.ctypes.data,
+                                     None, 0) == -4           # W % 80 != 0: not eligible
