@@ -2,7 +2,7 @@
 """Per-kernel SASS opcode histogram of libvhr_b200.so (cuobjdump -sass), written to
 profiles/sass_opcodes.txt: the evidence that the data movement is TMA / mbarrier based
 (UTMALDG = cp.async.bulk.tensor, UBLKCP = cp.async.bulk, SYNCS = mbarrier ops) and which math
-pipes each kernel uses (IMMA = mma.sync integer tensor tiles, IDP = dp4a/dp2a, FFMA ...).
+pipes each kernel uses (UTCIMMA = tcgen05.mma kind::i8, LDTM = tcgen05.ld, UTCBAR = tcgen05.commit, IMMA = mma.sync integer tensor tiles, IDP = dp4a/dp2a, FFMA ...).
 
     python tools/sass_histogram.py [--top 14]
 """
@@ -17,7 +17,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "video-heart-rate_b200", "csrc", "libvhr_b200.so")
-KEY = ("UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "IMMA", "HMMA", "IDP", "LDGSTS", "UTCHMMA", "LDTM")
+KEY = ("UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "UTCIMMA", "UTCHMMA", "UTCBAR", "LDTM", "IMMA", "HMMA", "IDP", "LDGSTS")
 
 
 def main():

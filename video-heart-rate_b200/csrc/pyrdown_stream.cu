@@ -1,24 +1,22 @@
-// Streaming fast path of the fused pyrDown cascade (W % 16 == 0, 16-byte aligned frames); the
-// generic kernel in pyrdown.cu covers every other shape with the same arithmetic.
+// Streaming CUDA-core form of the fused pyrDown cascade (W % 16 == 0; W % 64 == 0 for >= 3 levels; 16-byte aligned
+// frames).  Since round 2 it serves the shapes and level counts the tensor-core kernel (pyrdown_umma.cu: 4 levels,
+// W % 80 == 0) does not take; pyrdown_mma.cu and the generic kernel in pyrdown.cu cover the rest, same arithmetic.
 //
-// Same spec as pyrdown.cu (cv2.pyrDown float32 semantics; levels 1-2 exact integers * 2^-8l).
-// Layout of the work, driven by the ncu captures in profiles/ (the previous fast path spent two
-// thirds of its 4.4e9 warp-instructions on levels >= 2, which hold a quarter of the data, and
-// was issue-bound at 25 % of DRAM peak):
-//   * A thread owns a fixed column group: 8 input pixels -> 4 px of level 1 -> 2 px of level 2
-//     -> 1 px of levels >= 3, and streams rows top to bottom.  Levels 1 AND 2 live entirely in
-//     registers: level 1 = 4 IDP4A per value on the raw bytes + a packed-uint16 vertical pass on
-//     a register window; the finished level-1 row is handed to the level-2 horizontal pass
-//     (3 IDP2A per value) by WARP SHUFFLE (lanes 0 and 31 of each warp are halo lanes that
-//     recompute the neighbour warp's edge column, so warps never exchange level-1 data), and the
-//     level-2 vertical pass runs on a second register window.  Shared memory / block barriers are
-//     touched once per LEVEL-2 row (every 4 input rows), not once per row of every level.
-//   * Input rows arrive by cp.async.bulk (TMA engine, UBLKCP) into a shared-memory ring, one
-//     mbarrier per slot, issued up to a ring ahead by one thread: HBM requests in flight do not
-//     depend on registers or occupancy.  Each input byte is read from HBM once.
-//   * Levels >= 3 (1/16 of the data): horizontal-first with thread-private 5-row H rings in
-//     shared memory, newest finished row per level double-buffered, one barrier per produced row.
+// Same spec as pyrdown.cu (cv2.pyrDown float32 semantics; levels 1-2 exact integers * 2^-8l).  Current form (v6;
+// the stage-by-stage history with the ncu captures is in profiles/README.md, the design in DESIGN.md section 4.1b):
+//   * A thread owns a fixed column group: 8 input pixels -> 4 px of level 1 -> 2 px of level 2; a warp owns 30 groups,
+//     lanes 0 and 31 are halo lanes that recompute the neighbour warp's edge group.  Levels 1 and 2 live in registers.
+//     Level 1 runs its VERTICAL pass first, on the raw bytes split into packed 16-bit lanes with two incremental partial
+//     rows (A + 4 n1 + n2), so only one row per level-1 row goes through the horizontal pass (IDP2A on same-channel
+//     pixel pairs, neighbours by warp shuffle); the level-2 horizontal pass takes the finished level-1 row by shuffle.
+//   * Input per WARP: each warp has its own shared-memory ring of two-row groups, one cp.async.bulk.tensor.2d
+//     (UTMALDG.2D) per group on a per-group mbarrier; reflected rows at the frame's top / bottom by cp.async.bulk.
+//     No block barrier in the steady state.
+//   * Levels >= 3 (1/16 of the data) by ONE warp per level-2 row, in turn: every warp publishes its part of the
+//     finished level-2 row in a 4-slot ring (row mbarrier), the warp on duty runs the whole upper cascade for that row
+//     (duty mbarrier frees the slot).
 //   * Persistent grid over the flattened (frame, final-row) space, equal contiguous shares.
+// Bound by instruction issue (3.0e9 warp-instructions per 1080p clip, 73 % issue-active, 39 % of DRAM peak): 3.57 ms.
 #include "common.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
