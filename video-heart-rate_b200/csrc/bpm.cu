@@ -13,6 +13,7 @@
 //   vhr_sos_causal rppg_LIVESTREAM.py:226-251 live_sos_push (sosfilt with carried state)
 #include "common.cuh"
 #include "pairwise.cuh"
+#include <cooperative_groups.h>
 #include <math.h>
 
 namespace {
@@ -20,6 +21,8 @@ namespace {
 constexpr int BT = 256;
 constexpr int MAXSEC = 16;
 constexpr int MAXTAPS = 128;
+constexpr int MAXSPLIT = 8;        // CTAs (one thread-block cluster) sharing the bins of one window
+constexpr int MAXCOL = 8;          // columns of a (T,C) signal
 constexpr int MAXCOEF = (MAXSEC * 6 > MAXTAPS) ? MAXSEC * 6 : MAXTAPS;
 
 __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7FF8000000000000ll); }
@@ -129,17 +132,25 @@ struct FftArgs {
     int max_len;
 };
 
+// One thread-block CLUSTER per window: every CTA of the cluster loads and detrends the window (cheap, and it keeps the
+// pairwise-sum order), takes a contiguous share of the candidate bins, and CTA 0 merges the shares through
+// distributed shared memory in bin order (so ties still resolve to the lowest index, as np.argmax does).  A single
+// long window (the whole-clip estimate of the measurement plugins: 1 800 samples, 199 bins) no longer runs on one SM.
 __global__ void __launch_bounds__(BT) bpm_fft_kernel(const FftArgs a) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int nsplit = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
     extern __shared__ __align__(16) unsigned char sm[];
     __shared__ ArgMax shm[BT / 32];
+    __shared__ ArgMax share[MAXCOL];                                 // this CTA's best bin per column (read by CTA 0)
     double2* tw = reinterpret_cast<double2*>(sm);                    // [max_len]  (16-byte aligned first)
     double* x = reinterpret_cast<double*>(tw + a.max_len);           // [max_len]
     float* xf = reinterpret_cast<float*>(x + a.max_len);             // [max_len]
-    const int w = blockIdx.x;
+    const int w = blockIdx.x / nsplit;
     const int s = a.start[w], n = a.len[w];
     const bool bad = (n < 1) || n > a.max_len || s < 0 || s + n > a.n_trace || (a.mode == VHR_FFT_ANALYSIS && n < 8);
-    if (bad) {
-        if (threadIdx.x == 0) { a.bpm[w] = qnan(); a.bin[w] = -1; }
+    if (bad) {                                                       // the whole cluster takes this exit
+        if (threadIdx.x == 0 && rank == 0) { a.bpm[w] = qnan(); a.bin[w] = -1; }
         return;
     }
     for (int m = threadIdx.x; m < n; m += BT) {
@@ -154,9 +165,20 @@ __global__ void __launch_bounds__(BT) bpm_fft_kernel(const FftArgs a) {
     const int kpos = (n - 1) / 2;
     const int kmin = all_bins ? 0 : 1;
     const int kmax = all_bins ? n - 1 : kpos;
-    ArgMax best;
-    best.v = 0.;
-    best.k = -1;
+    // this CTA's share of the candidates: the in-band bins are one run k_lo..k_hi of the positive half (plus, in
+    // all_bins mode, anything else): split the index range evenly, ascending with the rank
+    int k_lo = kmin, k_hi = kmax;
+    if (!all_bins) {
+        // f(k) is monotonic in k: bisect with the very comparisons the bin loop makes
+        int lo = kmin, hi = kmax + 1;                   // first k with f(k) >= f_lo
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (np_freq(mid, n, a.fs) >= a.f_lo) hi = mid; else lo = mid + 1; }
+        k_lo = lo;
+        lo = kmin - 1; hi = kmax;                       // last k with f(k) <= f_hi
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (np_freq(mid, n, a.fs) <= a.f_hi) lo = mid; else hi = mid - 1; }
+        k_hi = lo;
+    }
+    const int per = (k_hi - k_lo + 1 + nsplit - 1) / nsplit;
+    const int my_lo = k_lo + rank * per, my_hi = min(k_hi, my_lo + per - 1);
     for (int c = 0; c < a.C; ++c) {
         __syncthreads();
         for (int i = threadIdx.x; i < n; i += BT) x[i] = a.trace[(size_t)(s + i) * a.ld + (size_t)c * a.cs];
@@ -166,7 +188,7 @@ __global__ void __launch_bounds__(BT) bpm_fft_kernel(const FftArgs a) {
         mine.v = 0.;
         mine.k = -1;
         // one warp per bin (long windows: a single window must not serialise 1800 samples per thread)
-        for (int k = kmin + (int)(threadIdx.x >> 5); k <= kmax; k += BT / 32) {
+        for (int k = my_lo + (int)(threadIdx.x >> 5); k <= my_hi; k += BT / 32) {
             const double f = np_freq(k <= kpos ? k : k - n, n, a.fs);
             if (f >= a.f_lo && f <= a.f_hi) {           // warp-uniform
                 // a negative-frequency bin has the magnitude of its mirror n - k (real input; NumPy's fft of a
@@ -176,13 +198,28 @@ __global__ void __launch_bounds__(BT) bpm_fft_kernel(const FftArgs a) {
             }
         }
         const ArgMax col = block_argmax(mine, shm);
-        // best channel: first maximum of the per-channel peak magnitudes
-        if (col.k >= 0 && (best.k < 0 || col.v > best.v)) best = col;
+        if (threadIdx.x == 0 && c < MAXCOL) share[c] = col;
     }
-    if (threadIdx.x == 0) {
+    cluster.sync();                                      // every CTA's shares are written
+    if (rank == 0 && threadIdx.x == 0) {
+        ArgMax best;
+        best.v = 0.;
+        best.k = -1;
+        for (int c = 0; c < a.C; ++c) {
+            ArgMax col;
+            col.v = 0.;
+            col.k = -1;
+            for (int r = 0; r < nsplit; ++r) {           // ascending bins: a later share wins only if strictly larger
+                const ArgMax o = *cluster.map_shared_rank(&share[c], r);
+                if (o.k >= 0 && (col.k < 0 || o.v > col.v)) col = o;
+            }
+            // best channel: first maximum of the per-channel peak magnitudes
+            if (col.k >= 0 && (best.k < 0 || col.v > best.v)) best = col;
+        }
         if (best.k < 0) { a.bpm[w] = qnan(); a.bin[w] = -1; }
         else { a.bpm[w] = __dmul_rn(np_freq(best.k <= kpos ? best.k : best.k - n, n, a.fs), 60.0); a.bin[w] = best.k; }
     }
+    cluster.sync();                                      // keep the shares alive until CTA 0 has read them
 }
 
 // ---- Welch path ----------------------------------------------------------------------------
@@ -421,7 +458,7 @@ extern "C" int vhr_bpm_fft(vhr_ctx* ctx, const double* d_trace, int n_trace, int
                            int detrend, int mode, double* d_bpm, int32_t* d_bin, void* stream) {
     VHR_REQUIRE(ctx, ctx != nullptr, "null context");
     VHR_REQUIRE(ctx, d_trace && d_start && d_len && d_bpm && d_bin, "null pointer");
-    VHR_REQUIRE(ctx, C >= 1 && cs >= 1 && ld >= 1 && fs > 0, "bad arguments");
+    VHR_REQUIRE(ctx, C >= 1 && C <= MAXCOL && cs >= 1 && ld >= 1 && fs > 0, "bad arguments (1..8 columns)");
     VHR_REQUIRE(ctx, detrend >= 0 && detrend <= 3 && (mode == 0 || mode == 1), "bad detrend/mode");
     int rc = check_windows(ctx, n_trace, n_win);
     if (rc != VHR_OK) return rc;
@@ -436,7 +473,23 @@ extern "C" int vhr_bpm_fft(vhr_ctx* ctx, const double* d_trace, int n_trace, int
         return VHR_ERR_UNSUPPORTED;
     }
     VHR_CHECK_CUDA(ctx, cudaFuncSetAttribute(bpm_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bpm_fft_kernel<<<n_win, BT, smem, (cudaStream_t)stream>>>(a);
+    // few windows: spread each over a cluster; many windows already fill the GPU (and the split repeats the detrend)
+    int nsplit = 1;
+    while (nsplit < MAXSPLIT && (long long)n_win * nsplit * 2 <= 2LL * ctx->num_sms) nsplit *= 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)n_win * nsplit, 1, 1);
+    cfg.blockDim = dim3(BT, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = nsplit;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VHR_CHECK_CUDA(ctx, cudaLaunchKernelEx(&cfg, bpm_fft_kernel, a));
     return vhr_after_launch(ctx, "bpm_fft_kernel");
 }
 
