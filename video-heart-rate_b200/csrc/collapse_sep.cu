@@ -33,6 +33,7 @@
 //   * ROI-only calls (no frame output requested, the measurement plugins' case) retire every
 //     item that touches no ROI before it requests a single pixel.
 #include "common.cuh"
+#include <type_traits>
 #include <stdlib.h>
 #include <math.h>
 #include <vector>
@@ -260,122 +261,151 @@ __global__ void __launch_bounds__(WARPS * 32, 2) collapse_sep_kernel(const SepAr
     const uint8_t* fnext = fwarp + (size_t)DEPTH * row_bytes;                 // TMA: next row to request
     const int nrows = y1 - y0;
 
-    for (int i = 0; i < nrows; ++i) {
-        const int y = y0 + i;
-        const int yb = __ldg(ybp + i);
-        const float4 wy = __ldg(ywp + i);
-        if (yb != cur) {                                 // warp-uniform; the host guarantees yb == cur + 1
-            cur = yb;
+    // RM == 2: the mask word of this lane's 4 pixels is fetched one row ahead (a dependent load per row and ROI stalled
+    // the items inside the bounding boxes: the polygon step ran 0.9 ms behind the rectangle one).  0 = no pixel of
+    // this lane inside ROI k on that row (only the rows / words of the bounding box were ever written).
+    uint32_t mnext[KMAXF > 0 ? KMAXF : 1];
+    auto mask_word = [&](int k, int y) -> uint32_t {
+        if (hit[k] && y >= ry1[k] && y < ry2[k] && y < y1 && X + 4 > rx1[k] && X < rx2[k])
+            return __ldg(a.mask + (moff[k] + (uint32_t)y * (uint32_t)a.MW));
+        return 0u;
+    };
+    if (KMAX > 0 && RM == 2 && any_hit && active) {
 #pragma unroll
-            for (int k = 0; k < 12; ++k) { Wn[0][k] = Wn[1][k]; Wn[1][k] = Wn[2][k]; Wn[2][k] = Wn[3][k]; }
-            hx_row(cur + 3, Wn[3]);
-            prefetch_lrow(cur + 4);
-        }
-        uint32_t w[3];
-        const int slot = i & (DEPTH - 1);
-        if (TMA) {
-            mbar_wait(bar_u32 + 8 * slot, (uint32_t)(i / DEPTH) & 1u);
-            const uint32_t* rp = reinterpret_cast<const uint32_t*>(ring + 384 * slot + lane_off);
-            w[0] = rp[0]; w[1] = rp[1]; w[2] = rp[2];
-        } else {
-            w[0] = pix[0][0]; w[1] = pix[0][1]; w[2] = pix[0][2];
-#pragma unroll
-            for (int j = 0; j + 1 < PF; ++j) { pix[j][0] = pix[j + 1][0]; pix[j][1] = pix[j + 1][1]; pix[j][2] = pix[j + 1][2]; }
-            load_pix(y + PF, pix[PF - 1]);
-        }
+        for (int k = 0; k < KMAX; ++k) mnext[k] = mask_word(k, y0);
+    }
 
-        float o[12];
-#pragma unroll
-        for (int k = 0; k < 12; ++k) {
-            // uint8 -> float: 0x4B0000xx = 2^23 + xx
-            float f = __uint_as_float(__byte_perm(w[k >> 2], 0x4B000000u, 0x7440 + (k & 3))) - 8388608.0f;
-            f = fmaf(wy.x, Wn[0][k], f);
-            f = fmaf(wy.y, Wn[1][k], f);
-            f = fmaf(wy.z, Wn[2][k], f);
-            f = fmaf(wy.w, Wn[3][k], f);
-            o[k] = f;
-        }
-
-        if (F32OUT && VEC) {
-            // the strip's previous bulk store must have finished reading it
-            float* strip = mystrips + (i & (NSTRIP - 1)) * 384;
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(NSTRIP - 1) : "memory");
-            __syncwarp();                                // strip free; every lane has read its ring slot
-            if (active) {
-                float4* sp = reinterpret_cast<float4*>(strip + 12 * lane);
-                sp[0] = make_float4(o[0], o[1], o[2], o[3]);
-                sp[1] = make_float4(o[4], o[5], o[6], o[7]);
-                sp[2] = make_float4(o[8], o[9], o[10], o[11]);
+    // The row loop exists twice: items that touch no ROI (88 % of them for a forehead + two cheeks) run an instance
+    // that carries none of the ROI state -- with the ROI registers live the loop body was 33 instructions longer for
+    // EVERY row (register shuffling at the 128-register cap), 1.0 ms per clip (profiles/README.md, round 2).
+    auto row_loop = [&](auto roi_c) {
+        constexpr bool ROI = decltype(roi_c)::value;
+        for (int i = 0; i < nrows; ++i) {
+            const int y = y0 + i;
+            const int yb = __ldg(ybp + i);
+            const float4 wy = __ldg(ywp + i);
+            if (yb != cur) {                                 // warp-uniform; the host guarantees yb == cur + 1
+                cur = yb;
+    #pragma unroll
+                for (int k = 0; k < 12; ++k) { Wn[0][k] = Wn[1][k]; Wn[1][k] = Wn[2][k]; Wn[2][k] = Wn[3][k]; }
+                hx_row(cur + 3, Wn[3]);
+                prefetch_lrow(cur + 4);
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy
-            __syncwarp();
-            if (elect_one()) {
-                bulk_s2g(owarp + (size_t)i * a.W * 3, smem_u32(strip), nbytes);
-                if (TMA && i + DEPTH < nrows) {
-                    mbar_expect_tx(bar_u32 + 8 * slot, seg_bytes);
-                    bulk_g2s(ring_u32 + 384 * slot, fnext + (size_t)i * row_bytes, seg_bytes, bar_u32 + 8 * slot);
-                }
-            }
-        } else {
-            if (F32OUT && active) {
-                float* dst = owarp + (size_t)i * a.W * 3 + 12 * lane;
-#pragma unroll
-                for (int k = 0; k < 12; ++k)
-                    if (X + k / 3 < a.W) dst[k] = o[k];
-            }
+            uint32_t w[3];
+            const int slot = i & (DEPTH - 1);
             if (TMA) {
-                __syncwarp();                            // every lane has read its ring slot
-                if (i + DEPTH < nrows && elect_one()) {
-                    mbar_expect_tx(bar_u32 + 8 * slot, seg_bytes);
-                    bulk_g2s(ring_u32 + 384 * slot, fnext + (size_t)i * row_bytes, seg_bytes, bar_u32 + 8 * slot);
+                mbar_wait(bar_u32 + 8 * slot, (uint32_t)(i / DEPTH) & 1u);
+                const uint32_t* rp = reinterpret_cast<const uint32_t*>(ring + 384 * slot + lane_off);
+                w[0] = rp[0]; w[1] = rp[1]; w[2] = rp[2];
+            } else {
+                w[0] = pix[0][0]; w[1] = pix[0][1]; w[2] = pix[0][2];
+    #pragma unroll
+                for (int j = 0; j + 1 < PF; ++j) { pix[j][0] = pix[j + 1][0]; pix[j][1] = pix[j + 1][1]; pix[j][2] = pix[j + 1][2]; }
+                load_pix(y + PF, pix[PF - 1]);
+            }
+
+            float o[12];
+    #pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                // uint8 -> float: 0x4B0000xx = 2^23 + xx
+                float f = __uint_as_float(__byte_perm(w[k >> 2], 0x4B000000u, 0x7440 + (k & 3))) - 8388608.0f;
+                f = fmaf(wy.x, Wn[0][k], f);
+                f = fmaf(wy.y, Wn[1][k], f);
+                f = fmaf(wy.z, Wn[2][k], f);
+                f = fmaf(wy.w, Wn[3][k], f);
+                o[k] = f;
+            }
+
+            if (F32OUT && VEC) {
+                // the strip's previous bulk store must have finished reading it
+                float* strip = mystrips + (i & (NSTRIP - 1)) * 384;
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(NSTRIP - 1) : "memory");
+                __syncwarp();                                // strip free; every lane has read its ring slot
+                if (active) {
+                    float4* sp = reinterpret_cast<float4*>(strip + 12 * lane);
+                    sp[0] = make_float4(o[0], o[1], o[2], o[3]);
+                    sp[1] = make_float4(o[4], o[5], o[6], o[7]);
+                    sp[2] = make_float4(o[8], o[9], o[10], o[11]);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy
+                __syncwarp();
+                if (elect_one()) {
+                    bulk_s2g(owarp + (size_t)i * a.W * 3, smem_u32(strip), nbytes);
+                    if (TMA && i + DEPTH < nrows) {
+                        mbar_expect_tx(bar_u32 + 8 * slot, seg_bytes);
+                        bulk_g2s(ring_u32 + 384 * slot, fnext + (size_t)i * row_bytes, seg_bytes, bar_u32 + 8 * slot);
+                    }
+                }
+            } else {
+                if (F32OUT && active) {
+                    float* dst = owarp + (size_t)i * a.W * 3 + 12 * lane;
+    #pragma unroll
+                    for (int k = 0; k < 12; ++k)
+                        if (X + k / 3 < a.W) dst[k] = o[k];
+                }
+                if (TMA) {
+                    __syncwarp();                            // every lane has read its ring slot
+                    if (i + DEPTH < nrows && elect_one()) {
+                        mbar_expect_tx(bar_u32 + 8 * slot, seg_bytes);
+                        bulk_g2s(ring_u32 + 384 * slot, fnext + (size_t)i * row_bytes, seg_bytes, bar_u32 + 8 * slot);
+                    }
                 }
             }
-        }
-        if (U8OUT && active) {
-            uint32_t qv[3] = {0, 0, 0};
-#pragma unroll
-            for (int k = 0; k < 12; ++k) {
-                const float v = fminf(fmaxf(o[k], 0.0f), 255.0f);
-                qv[k >> 2] |= (uint32_t)(int)(v + 0.5f) << (8 * (k & 3));
+            if (U8OUT && active) {
+                uint32_t qv[3] = {0, 0, 0};
+    #pragma unroll
+                for (int k = 0; k < 12; ++k) {
+                    const float v = fminf(fmaxf(o[k], 0.0f), 255.0f);
+                    qv[k >> 2] |= (uint32_t)(int)(v + 0.5f) << (8 * (k & 3));
+                }
+                uint8_t* dst = ulane + (size_t)i * row_bytes;
+                if (VEC) {
+                    uint32_t* op = reinterpret_cast<uint32_t*>(dst);
+                    op[0] = qv[0]; op[1] = qv[1]; op[2] = qv[2];
+                } else {
+    #pragma unroll
+                    for (int k = 0; k < 12; ++k)
+                        if (X + k / 3 < a.W) dst[k] = (uint8_t)(qv[k >> 2] >> (8 * (k & 3)));
+                }
             }
-            uint8_t* dst = ulane + (size_t)i * row_bytes;
-            if (VEC) {
-                uint32_t* op = reinterpret_cast<uint32_t*>(dst);
-                op[0] = qv[0]; op[1] = qv[1]; op[2] = qv[2];
-            } else {
-#pragma unroll
-                for (int k = 0; k < 12; ++k)
-                    if (X + k / 3 < a.W) dst[k] = (uint8_t)(qv[k >> 2] >> (8 * (k & 3)));
-            }
-        }
-        if (KMAX > 0 && any_hit && active) {
-#pragma unroll
-            for (int k = 0; k < KMAX; ++k) {
-                if (hit[k] && y >= ry1[k] && y < ry2[k]) {
-                    if (RM == 2) {
-                        // 4 mask bits of this lane's pixels (X % 4 == 0: they never straddle a word); only the
-                        // words of the bounding box were written, lanes outside it do not read
-                        if (X + 4 > rx1[k] && X < rx2[k]) {
-                            const uint32_t mw = __ldg(a.mask + (moff[k] + (uint32_t)y * (uint32_t)a.MW));
-                            const uint32_t bits = (mw >> (X & 31)) & 0xFu;
-#pragma unroll
-                            for (int px = 0; px < 4; ++px) {
-                                if ((bits >> px) & 1u) {
-                                    acc[k][0] += o[3 * px]; acc[k][1] += o[3 * px + 1]; acc[k][2] += o[3 * px + 2];
-                                }
-                            }
-                        }
-                    } else {
-#pragma unroll
+            if (ROI && RM == 2 && any_hit && active) {
+    #pragma unroll
+                for (int k = 0; k < KMAX; ++k) {
+                    // 4 mask bits of this lane's pixels (X % 4 == 0: they never straddle a word)
+                    const uint32_t bits = (mnext[k] >> (X & 31)) & 0xFu;
+                    mnext[k] = mask_word(k, y + 1);
+                    if (bits) {
+    #pragma unroll
                         for (int px = 0; px < 4; ++px) {
-                            if (X + px >= rx1[k] && X + px < rx2[k] && X + px < a.W) {
+                            if ((bits >> px) & 1u) {
                                 acc[k][0] += o[3 * px]; acc[k][1] += o[3 * px + 1]; acc[k][2] += o[3 * px + 2];
                             }
                         }
                     }
                 }
             }
+            if (ROI && RM != 2 && any_hit && active) {
+    #pragma unroll
+                for (int k = 0; k < KMAX; ++k) {
+                    if (hit[k] && y >= ry1[k] && y < ry2[k]) {
+                        {
+    #pragma unroll
+                            for (int px = 0; px < 4; ++px) {
+                                if (X + px >= rx1[k] && X + px < rx2[k] && X + px < a.W) {
+                                    acc[k][0] += o[3 * px]; acc[k][1] += o[3 * px + 1]; acc[k][2] += o[3 * px + 2];
+                                }
+                            }
+                        }
+                    }
+                }
+            }
         }
+    };
+    if constexpr (KMAX > 1) {
+        if (any_hit) row_loop(std::true_type{});
+        else row_loop(std::false_type{});
+    } else {
+        row_loop(std::integral_constant<bool, (KMAX > 0)>{});      // one ROI: its state is cheap, one instance (8.90 vs 9.03 ms)
     }
     if (VEC && F32OUT && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 

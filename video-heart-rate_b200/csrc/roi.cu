@@ -197,6 +197,8 @@ __global__ void __launch_bounds__(RT) poly_mean_kernel(const Tpix* __restrict__ 
         bx0 = min(bx0, verts[i].x); bx1 = max(bx1, verts[i].x);
         by0 = min(by0, verts[i].y); by1 = max(by1, verts[i].y);
     }
+    // every |coordinate| and every row <= 16383: the 32-bit form of the edge arithmetic is exact
+    const bool small = n > 0 && bx0 >= -16383 && by0 >= -16383 && bx1 <= 16383 && by1 <= 16383 && H <= 16383;
     bx0 = max(bx0, 0); by0 = max(by0, 0); bx1 = min(bx1, W - 1); by1 = min(by1, H - 1);
     const int bw = bx1 - bx0 + 1, bh = by1 - by0 + 1;
     const Tpix* fr = frames + (size_t)t * H * W * 3;
@@ -246,15 +248,15 @@ __global__ void __launch_bounds__(RT) poly_mean_kernel(const Tpix* __restrict__ 
 // One warp per row, one lane per edge; the row mask lives in shared memory as bits.
 constexpr int SCAN_MAXW = 256;          // mask words per row: bounding boxes up to 8192 pixels wide
 
-__device__ __forceinline__ void scan_row_mask(int y, const int2* __restrict__ v, int n, int bx0, int bw,
-                                              uint32_t* __restrict__ tog, uint32_t* __restrict__ edg) {
+// I = long long in general; int when every coordinate (and y) lies within +-16383, so that dx (y - y0) < 2^31: a 64-bit
+// integer division costs ~100 instructions, and the three per edge and row were the whole cost of the row-mask kernel.
+template <typename I>
+__device__ __forceinline__ void scan_row_edges(int y, const int2* __restrict__ v, int n, int bx0, int bw,
+                                               uint32_t* __restrict__ tog, uint32_t* __restrict__ edg) {
     const int lane = threadIdx.x & 31;
-    const int nw = (bw + 31) >> 5;
-    for (int w = lane; w < nw; w += 32) { tog[w] = 0u; edg[w] = 0u; }
-    __syncwarp();
     for (int e = lane; e < n; e += 32) {
         const int2 a = v[e], b = v[e + 1 == n ? 0 : e + 1];
-        const long long dx = (long long)b.x - a.x, dy = (long long)b.y - a.y;
+        const I dx = (I)b.x - a.x, dy = (I)b.y - a.y;
         if (dy == 0) {
             if (a.y == y) {                                         // horizontal edge (or a repeated vertex) on this row
                 const int c0 = max(min(a.x, b.x), bx0) - bx0, c1 = min(max(a.x, b.x), bx0 + bw - 1) - bx0;
@@ -265,15 +267,19 @@ __device__ __forceinline__ void scan_row_mask(int y, const int2* __restrict__ v,
             }
             continue;
         }
-        long long num = dx * ((long long)y - a.y), den = dy;
+        const bool on_span = y >= min(a.y, b.y) && y <= max(a.y, b.y);
+        const bool straddles = (a.y <= y) != (b.y <= y);
+        if (!on_span && !straddles) continue;                        // (a straddling edge is always on the span)
+        I num = dx * ((I)y - a.y), den = dy;
         if (den < 0) { num = -num; den = -den; }
-        if (y >= min(a.y, b.y) && y <= max(a.y, b.y) && num % den == 0) {       // lattice point of the segment on this row
-            const long long x = (long long)a.x + num / den;
+        const I quo = num / den, rem = num - quo * den;              // truncated division, one divide
+        if (on_span && rem == 0) {                                   // lattice point of the segment on this row
+            const long long x = (long long)a.x + (long long)quo;
             if (x >= bx0 && x < (long long)bx0 + bw) atomicOr(&edg[(int)(x - bx0) >> 5], 1u << ((int)(x - bx0) & 31));
         }
-        if ((a.y <= y) != (b.y <= y)) {
-            long long q = num / den;                                 // ceil(num / den), den > 0
-            if (num > 0 && num % den != 0) ++q;
+        if (straddles) {
+            long long q = (long long)quo;                            // ceil(num / den), den > 0
+            if (num > 0 && rem != 0) ++q;
             const long long xi = (long long)a.x + q;                 // pixels x < xi are left of the crossing
             if (xi < (long long)bx0 + bw) {
                 const int c = xi <= bx0 ? 0 : (int)(xi - bx0);
@@ -281,6 +287,16 @@ __device__ __forceinline__ void scan_row_mask(int y, const int2* __restrict__ v,
             }
         }
     }
+}
+
+__device__ __forceinline__ void scan_row_mask(int y, const int2* __restrict__ v, int n, int bx0, int bw,
+                                              uint32_t* __restrict__ tog, uint32_t* __restrict__ edg, bool small = false) {
+    const int lane = threadIdx.x & 31;
+    const int nw = (bw + 31) >> 5;
+    for (int w = lane; w < nw; w += 32) { tog[w] = 0u; edg[w] = 0u; }
+    __syncwarp();
+    if (small) scan_row_edges<int>(y, v, n, bx0, bw, tog, edg);
+    else scan_row_edges<long long>(y, v, n, bx0, bw, tog, edg);
     __syncwarp();
     // inclusive prefix-XOR along the row, 32 words per step
     uint32_t carry = 0u;                                             // parity of all toggles in the words before this step
@@ -325,6 +341,8 @@ __global__ void __launch_bounds__(RT) poly_mean_scan_kernel(const Tpix* __restri
         bx0 = min(bx0, verts[i].x); bx1 = max(bx1, verts[i].x);
         by0 = min(by0, verts[i].y); by1 = max(by1, verts[i].y);
     }
+    // every |coordinate| and every row <= 16383: the 32-bit form of the edge arithmetic is exact
+    const bool small = n > 0 && bx0 >= -16383 && by0 >= -16383 && bx1 <= 16383 && by1 <= 16383 && H <= 16383;
     bx0 = max(bx0, 0); by0 = max(by0, 0); bx1 = min(bx1, W - 1); by1 = min(by1, H - 1);
     const int bw = bx1 - bx0 + 1, bh = by1 - by0 + 1;
     const Tpix* fr = frames + (size_t)t * H * W * 3;
@@ -335,7 +353,7 @@ __global__ void __launch_bounds__(RT) poly_mean_scan_kernel(const Tpix* __restri
         uint32_t* tog = rowmask[warp][0];
         uint32_t* edg = rowmask[warp][1];
         for (int y = by0 + warp; y <= by1; y += RT / 32) {
-            scan_row_mask(y, verts, n, bx0, bw, tog, edg);
+            scan_row_mask(y, verts, n, bx0, bw, tog, edg, small);
             const Tpix* row = fr + ((size_t)y * W + bx0) * 3;
             for (int c0 = 0; c0 < bw; c0 += 32) {
                 const uint32_t m = tog[c0 >> 5];                     // warp-uniform word
@@ -390,6 +408,8 @@ __global__ void __launch_bounds__(RT) poly_rowmask_kernel(int H, int W, const in
         bx0 = min(bx0, verts[i].x); bx1 = max(bx1, verts[i].x);
         by0 = min(by0, verts[i].y); by1 = max(by1, verts[i].y);
     }
+    // every |coordinate| and every row <= 16383: the 32-bit form of the edge arithmetic is exact
+    const bool small = n > 0 && bx0 >= -16383 && by0 >= -16383 && bx1 <= 16383 && by1 <= 16383 && H <= 16383;
     bx0 = max(bx0, 0); by0 = max(by0, 0); bx1 = min(bx1, W - 1); by1 = min(by1, H - 1);
     const bool some = n > 0 && bx1 >= bx0 && by1 >= by0;
     unsigned long long cnt = 0;
@@ -402,7 +422,7 @@ __global__ void __launch_bounds__(RT) poly_rowmask_kernel(int H, int W, const in
         uint32_t* edg = rowmask[warp][1];
         uint32_t* dst = mask + (size_t)tk * H * MW + (ax0 >> 5);
         for (int y = by0 + warp; y <= by1; y += RT / 32) {
-            scan_row_mask(y, verts, n, ax0, bw, tog, edg);
+            scan_row_mask(y, verts, n, ax0, bw, tog, edg, small);
             for (int w = lane; w < nw; w += 32) {
                 const uint32_t m = tog[w];
                 dst[(size_t)y * MW + w] = m;
