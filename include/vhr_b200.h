@@ -89,6 +89,11 @@ int vhr_pyrdown_cascade(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int
  * UMMA K-major core-matrix layout.  VHR_ERR_UNSUPPORTED when the shape is not eligible. */
 int vhr_pyrdown_umma_plan(int H, int W, int32_t* tiles, int32_t* codes, int32_t* wsp, int32_t* meta,
                           uint8_t* blob, int blob_cap);
+/* Diagnostics: the 4-level cascade through the tensor-core kernel, which also copies the raw TMEM accumulators of one
+ * (item, strip) to d_acc (128 x 240 uint32; item = frame * tiles + tile): exact integers (the vertical 13-tap sums of
+ * the tile's level-2 rows over the strip's 240 byte columns), so a test holds the MMA stage to the plan bit for bit. */
+int vhr_pyrdown_umma_accumulators(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int W, float* d_level,
+                                  int item, int strip, uint32_t* d_acc, void* stream);
 
 /* ---- EVM: temporal ideal bandpass (no reference code; spec = irfft(mask*rfft)) ----------
  * d_in/d_out float32 (T,P), time-major; keeps rfft bins with f_lo <= k*fps/T <= f_hi

@@ -162,6 +162,37 @@ def test_pyrdown_tensor_core_kernel(vhr, eng, case, monkeypatch):
         np.testing.assert_array_equal(got2, np.concatenate([got[-2:], got[:-2]]))
 
 
+@pytest.mark.parametrize("case", [(2, 1080, 1920), (3, 720, 1280), (2, 90, 720)])
+def test_pyrdown_tensor_core_accumulators_are_exact(vhr, eng, case):
+    """The MMA stage alone: the raw TMEM accumulators of a few (item, strip) pairs -- first / interior / flush strip,
+    top / bottom tile -- equal the integer product of the plan's weight slices with the image rows, bit for bit (TMA box
+    layout, 128-byte swizzle, shared-memory descriptors, band offsets, baked reflect-101 borders)."""
+    import sys
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tools", "probes"))
+    import umma_emulate as em
+    T, H, W = case
+    rng = np.random.default_rng(H + W)
+    fr = rng.integers(0, 256, (T, H, W, 3), dtype=np.uint8)
+    frd = torch.as_tensor(fr, device=eng.tdev)
+    plan = em.make_plan(H, W)
+    nt, S = len(plan["tiles"]), plan["nstrips"]
+    for item, strip in ((0, 0), (0, 1), (nt - 1, S - 2), (T * nt - 1, S - 1), (nt, S // 2)):
+        _, acc = eng.pyrdown_tc_accumulators(frd, item, strip)
+        f, t = divmod(item, nt)
+        tile = plan["tiles"][t]
+        img = fr[f].reshape(H, W * 3).astype(np.int64)
+        D = np.zeros((128, 240), dtype=np.int64)
+        for ks in range(tile["nks"]):
+            rows = tile["i0"] + 32 * ks + np.arange(32)
+            B = np.zeros((32, 240), dtype=np.int64)
+            ok = (rows >= 0) & (rows < H)
+            seg = img[rows[ok], 240 * strip: 240 * strip + 240]
+            B[ok, :seg.shape[1]] = seg
+            D += tile["slices"][ks] @ B
+        np.testing.assert_array_equal(acc.cpu().numpy()[:tile["nr"]], D[:tile["nr"]])
+
+
 def test_pyrdown_tensor_core_kernel_constant_and_extremes(vhr, eng):
     """All-255 frames exercise the largest accumulators (255 * 256 per column, 255 * 65536 per level-2 value): every level
     of a constant image is that constant, exactly; a single bright pixel checks every weight of the composite filters."""

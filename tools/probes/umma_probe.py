@@ -32,12 +32,8 @@ def main():
     res = {"H": H, "W": W, "T": T}
     # 1. raw accumulators
     for item, strip in ((0, 1), (len(plan["tiles"]) - 1, 0), (0, plan["nstrips"] - 2)):
-        dbg = torch.full((128, 240), 0xDEAD, dtype=torch.int32, device=eng.tdev)
-        os.environ["VHR_UMMA_DEBUG"] = f"{dbg.data_ptr()},{item},{strip}"
-        os.environ["VHR_PYRDOWN_IMPL"] = "umma"
-        out = eng.pyrdown(frd, 4)
+        out, dbg = eng.pyrdown_tc_accumulators(frd, item, strip)
         torch.cuda.synchronize()
-        del os.environ["VHR_UMMA_DEBUG"]
         f, t = divmod(item, len(plan["tiles"]))
         tile = plan["tiles"][t]
         img = fr[f].reshape(H, W * 3).astype(np.int64)

@@ -30,6 +30,7 @@ SIGNATURES = {
     "vhr_pyr_dims": (c_int, [c_int, c_int, c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "vhr_pyrdown_cascade": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "vhr_pyrdown_umma_plan": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
+    "vhr_pyrdown_umma_accumulators": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "vhr_temporal_bandpass": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_double, c_double,
                                       c_double, c_float, c_void_p]),
     "vhr_band_bins": (c_int, [c_int, c_double, c_double, c_double, C.POINTER(c_int), C.POINTER(c_int)]),

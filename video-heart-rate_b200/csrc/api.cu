@@ -106,7 +106,7 @@ int vhr_destroy(vhr_ctx* ctx) {
     if (ctx->mask) cudaFree(ctx->mask);
     if (ctx->hostpath) cudaFree(ctx->hostpath);
     if (ctx->sep_tab) cudaFree(ctx->sep_tab);
-    if (ctx->umma_blob) cudaFree(ctx->umma_blob);
+    for (int i = 0; i < ctx->umma_n; ++i) if (ctx->umma_blob[i]) cudaFree(ctx->umma_blob[i]);
     if (ctx->last_ev) cudaEventDestroy(ctx->last_ev);
     if (ctx->hp_copy) cudaStreamDestroy(ctx->hp_copy);
     if (ctx->hp_comp) cudaStreamDestroy(ctx->hp_comp);

@@ -37,9 +37,13 @@ struct vhr_ctx {
     void* sep_tab = nullptr;
     size_t sep_tab_bytes = 0;
     long long sep_key = -1;
-    // weight band + border slices of the tensor-core pyrDown (pyrdown_umma.cu), keyed by frame shape
-    void* umma_blob = nullptr;
-    long long umma_key = -1;
+    // weight bands + border slices of the tensor-core pyrDown (pyrdown_umma.cu), one read-only blob per frame shape.
+    // A blob is never rewritten or freed while the context lives (kernels on any stream may be reading it); when the
+    // table is full the whole device is synchronised before the oldest entry is replaced.
+    static constexpr int UMMA_SLOTS = 8;
+    void* umma_blob[UMMA_SLOTS] = {nullptr};
+    long long umma_key[UMMA_SLOTS] = {0};
+    int umma_n = 0, umma_next = 0;
 };
 
 void vhr_set_error(vhr_ctx* ctx, const char* fmt, ...);

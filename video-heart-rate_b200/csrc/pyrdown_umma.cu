@@ -664,10 +664,11 @@ extern "C" int vhr_pyrdown_umma_plan(int H, int W, int32_t* tiles, int32_t* code
     return VHR_OK;
 }
 
-int vhr_pyrdown_umma(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int W, int levels, float* d_level, cudaStream_t stream) {
+static int umma_launch(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int W, int levels, float* d_level, cudaStream_t stream,
+                       uint32_t* d_acc, int acc_item, int acc_strip) {
     if (levels != 4 || (reinterpret_cast<uintptr_t>(d_frames) & 15) != 0) return VHR_ERR_UNSUPPORTED;
     if (SMEM_BYTES > ctx->smem_optin) return VHR_ERR_UNSUPPORTED;
-    // plan + blob cached per shape (the blob is uploaded once; vhr_enter / vhr_leave order its use across streams)
+    // plan cached per thread and shape, blob cached per context and shape
     static thread_local UmmaPlan plan;
     if (plan.H != H || plan.W != W) {
         UmmaPlan p;
@@ -676,14 +677,23 @@ int vhr_pyrdown_umma(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int W,
         plan = p;
     }
     const long long key = ((long long)H << 32) | (unsigned)W;
-    if (ctx->umma_key != key || !ctx->umma_blob) {
-        VHR_CHECK_CUDA(ctx, cudaStreamSynchronize(stream));
-        if (ctx->last_stream && ctx->last_stream != stream) VHR_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->last_stream));
-        if (ctx->umma_blob) cudaFree(ctx->umma_blob);
-        ctx->umma_blob = nullptr;
-        VHR_CHECK_CUDA(ctx, cudaMalloc(&ctx->umma_blob, BAND_BYTES + MAX_SPECIAL * SLICE_BYTES));
-        VHR_CHECK_CUDA(ctx, cudaMemcpy(ctx->umma_blob, plan.blob.data(), plan.blob.size(), cudaMemcpyHostToDevice));
-        ctx->umma_key = key;
+    const uint8_t* d_blob = nullptr;
+    for (int i = 0; i < ctx->umma_n && !d_blob; ++i)
+        if (ctx->umma_key[i] == key) d_blob = static_cast<const uint8_t*>(ctx->umma_blob[i]);
+    if (!d_blob) {
+        int slot = ctx->umma_n;
+        if (slot == vhr_ctx::UMMA_SLOTS) {                 // table full: nothing may still be reading the entry we replace
+            VHR_CHECK_CUDA(ctx, cudaDeviceSynchronize());
+            slot = ctx->umma_next;
+            ctx->umma_next = (ctx->umma_next + 1) % vhr_ctx::UMMA_SLOTS;
+        } else {
+            VHR_CHECK_CUDA(ctx, cudaMalloc(&ctx->umma_blob[slot], BAND_BYTES + MAX_SPECIAL * SLICE_BYTES));
+            ctx->umma_n = slot + 1;
+        }
+        // synchronous copy into memory no kernel reads yet; kernels launched after this call see it on any stream
+        VHR_CHECK_CUDA(ctx, cudaMemcpy(ctx->umma_blob[slot], plan.blob.data(), plan.blob.size(), cudaMemcpyHostToDevice));
+        ctx->umma_key[slot] = key;
+        d_blob = static_cast<const uint8_t*>(ctx->umma_blob[slot]);
     }
     static PFN_cuTensorMapEncodeTiled encode = nullptr;
     if (!encode) {
@@ -711,18 +721,14 @@ int vhr_pyrdown_umma(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int W,
     a.h2 = plan.h[2]; a.h3 = plan.h[3]; a.h4 = plan.h[4]; a.w4 = plan.w[4];
     a.nstrips = plan.nstrips; a.ntiles = plan.ntiles;
     a.items = (long long)T * plan.ntiles;
-    a.blob = static_cast<const uint8_t*>(ctx->umma_blob);
+    a.blob = d_blob;
     a.blob_bytes = (int)plan.blob.size();
     for (int t = 0; t < plan.ntiles; ++t) {
         a.tile[t] = plan.tile[t];
         for (int ks = 0; ks < MAX_KS; ++ks) a.code[t][ks] = plan.code[t][ks];
     }
     memcpy(a.wsp, plan.wsp, sizeof(a.wsp));
-    const char* dbg = getenv("VHR_UMMA_DEBUG");       // "<device pointer>,<item>,<strip>" (tools/probes)
-    if (dbg) {
-        unsigned long long ptr = 0; int it = 0, st = 0;
-        if (sscanf(dbg, "%llu,%d,%d", &ptr, &it, &st) == 3) { a.dbg = reinterpret_cast<uint32_t*>(ptr); a.dbg_item = it; a.dbg_strip = st; }
-    }
+    a.dbg = d_acc; a.dbg_item = acc_item; a.dbg_strip = acc_strip;
     const char* mode = getenv("VHR_UMMA_MODE");
     a.mode = mode ? atoi(mode) : 0;
     auto kern = a.dbg ? pyrdown_umma_kernel<true> : pyrdown_umma_kernel<false>;
@@ -731,4 +737,20 @@ int vhr_pyrdown_umma(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int W,
     if (grid > a.items) grid = a.items;
     kern<<<(int)grid, THREADS, SMEM_BYTES, stream>>>(a, tmap);
     return vhr_after_launch(ctx, "pyrdown_umma_kernel");
+}
+
+int vhr_pyrdown_umma(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int W, int levels, float* d_level, cudaStream_t stream) {
+    return umma_launch(ctx, d_frames, T, H, W, levels, d_level, stream, nullptr, 0, 0);
+}
+
+// Diagnostics (tests): the cascade through the tensor-core kernel, which also copies the raw TMEM accumulators of one
+// (item, strip) -- item = frame * tiles + tile -- to d_acc (128 x 240 uint32: the vertical 13-tap sums of the tile's
+// level-2 rows over the strip's 240 byte columns).  They are exact integers, so a test can hold the MMA stage (tensor map,
+// swizzle, descriptors, baked border weights) to the plan bit for bit.  VHR_ERR_UNSUPPORTED when the shape is not eligible.
+extern "C" int vhr_pyrdown_umma_accumulators(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int W, float* d_level, int item,
+                                             int strip, uint32_t* d_acc, void* stream) {
+    VHR_REQUIRE(ctx, ctx != nullptr, "null context");
+    VHR_REQUIRE(ctx, d_frames && d_level && d_acc, "null pointer");
+    VHR_REQUIRE(ctx, T >= 1 && H >= 1 && W >= 1 && item >= 0 && strip >= 0, "bad arguments");
+    return umma_launch(ctx, d_frames, T, H, W, 4, d_level, (cudaStream_t)stream, d_acc, item, strip);
 }

@@ -116,6 +116,19 @@ class Engine:
                                                  self._stream()), "vhr_pyrdown_cascade")
         return out
 
+    def pyrdown_tc_accumulators(self, frames, item: int, strip: int):
+        """Diagnostics: the 4-level cascade through the tensor-core kernel plus the raw TMEM accumulators (128, 240) int32 of
+        one (item, strip) -- include/vhr_b200.h:vhr_pyrdown_umma_accumulators.  Raises on shapes the kernel does not take."""
+        torch = _torch()
+        assert frames.dtype == torch.uint8 and frames.is_cuda and frames.is_contiguous() and frames.shape[-1] == 3
+        T, H, W, _ = frames.shape
+        wl, hl = self.pyr_dims(W, H, 4)[-1]
+        out = torch.empty((T, hl, wl, 3), dtype=torch.float32, device=self.tdev)
+        acc = torch.zeros((128, 240), dtype=torch.int32, device=self.tdev)
+        self._check(self.lib.vhr_pyrdown_umma_accumulators(self.ctx, self._p(frames), T, H, W, self._p(out), int(item), int(strip),
+                                                           self._p(acc), self._stream()), "vhr_pyrdown_umma_accumulators")
+        return out, acc
+
     def band_bins(self, T: int, fps: float, f_lo: float, f_hi: float):
         k0, k1 = C.c_int(-1), C.c_int(-1)
         n = self.lib.vhr_band_bins(T, fps, f_lo, f_hi, C.byref(k0), C.byref(k1))
