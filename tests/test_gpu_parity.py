@@ -102,11 +102,10 @@ def test_pyrdown_many_frames_persistent_split(vhr, eng):
                                   (3, 90, 720, 4), (6, 61, 1296, 3), (2, 48, 3072, 4), (30, 40, 96, 5), (4, 135, 240, 1),
                                   (700, 40, 64, 2), (9, 270, 480, 4), (3, 135, 2048, 4), (5, 97, 176, 2), (7, 67, 1280, 4)])
 def test_pyrdown_streaming_kernels(vhr, eng, case, monkeypatch):
-    """The two streaming kernels on shapes that exercise shares crossing frames, wide frames, 5 and 6 levels, odd level
-    heights, widths only one of them takes (W % 64 != 0: tensor-core kernel only; 6 levels or W % 2^L != 0: streaming
-    kernel only): pyrdown_stream.cu (registers + shuffles for levels 1-2, per-warp TMA input rings, upper levels by one warp in turn)
-    and pyrdown_mma.cu (banded 5-tap on IMMA tiles, one private pipeline per warp).  Each is held to the
-    oracle; where both apply they agree bit for bit on levels 1-2 and to 1e-6 above."""
+    """The CUDA-core kernels on shapes that exercise shares crossing frames, wide frames, 5 and 6 levels, odd level heights
+    and widths the streaming kernel does not take (W % 64 != 0 with >= 3 levels: the generic kernel steps in):
+    pyrdown_stream.cu (registers + shuffles for levels 1-2, per-warp TMA input rings, upper levels by one warp in turn) and
+    the generic kernel of pyrdown.cu.  Each is held to the oracle; they agree bit for bit on levels 1-2 and to 1e-6 above."""
     import torch
     T, H, W, levels = case
     rng = np.random.default_rng(T + H + W + levels)
@@ -116,10 +115,10 @@ def test_pyrdown_streaming_kernels(vhr, eng, case, monkeypatch):
     sel = np.r_[0:n_ref // 2, T - (n_ref - n_ref // 2):T]
     ref = oevm.pyrdown_cascade(fr[sel], levels)
     outs = {}
-    for impl in ("stream", "mma"):                            # (the tcgen05 kernel has its own test below)
-        monkeypatch.setenv("VHR_PYRDOWN_IMPL", impl)
+    for impl, var, val in (("stream", "VHR_PYRDOWN_IMPL", "stream"), ("generic", "VHR_PYRDOWN_GENERIC", "1")):
+        monkeypatch.setenv(var, val)                          # (the tcgen05 kernel has its own tests below)
         got = eng.pyrdown(frd, levels).cpu().numpy()
-        monkeypatch.delenv("VHR_PYRDOWN_IMPL")
+        monkeypatch.delenv(var)
         assert got.shape[1:] == ref.shape[1:]
         if levels <= 2:
             np.testing.assert_array_equal(got[sel], ref.astype(np.float32))
@@ -127,9 +126,9 @@ def test_pyrdown_streaming_kernels(vhr, eng, case, monkeypatch):
             assert rel_err(got[sel], ref) <= REL
         outs[impl] = got
     if levels <= 2:
-        np.testing.assert_array_equal(outs["stream"], outs["mma"])
+        np.testing.assert_array_equal(outs["stream"], outs["generic"])
     else:
-        assert rel_err(outs["stream"], outs["mma"]) <= 1e-6   # every frame, every share boundary
+        assert rel_err(outs["stream"], outs["generic"]) <= 1e-6   # every frame, every share boundary
 
 
 @pytest.mark.parametrize("case", [(5, 1080, 1920), (4, 720, 1280), (7, 480, 640), (300, 67, 1280), (9, 1081, 160), (3, 2160, 320),
@@ -147,7 +146,7 @@ def test_pyrdown_tensor_core_kernel(vhr, eng, case, monkeypatch):
     monkeypatch.setenv("VHR_PYRDOWN_IMPL", "umma")
     got = eng.pyrdown(frd, 4).cpu().numpy()
     assert eng.launch_count() == before + 1
-    monkeypatch.setenv("VHR_PYRDOWN_IMPL", "stream" if W % 64 == 0 else "mma")
+    monkeypatch.setenv("VHR_PYRDOWN_IMPL", "stream")          # (W % 64 != 0: the generic kernel)
     other = eng.pyrdown(frd, 4).cpu().numpy()
     monkeypatch.delenv("VHR_PYRDOWN_IMPL")
     n_ref = min(T, 4)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """pyrDown cascade alone on one 1080p / 1800-frame clip resident in HBM: CUDA-event time per kernel variant and level
-count (VHR_PYRDOWN_IMPL = stream | mma | umma).  One JSON line."""
+count (VHR_PYRDOWN_IMPL = umma | stream).  One JSON line."""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -14,7 +14,7 @@ def main():
     W, H = int(os.environ.get("PYR_W", 1920)), int(os.environ.get("PYR_H", 1080))
     fr = eng.synth_clip(vhr.SynthSpec(T=T, H=H, W=W, fps=30.0, pulse_hz=1.2, seed=0, clip=0))
     res = {"T": T, "W": W, "H": H}
-    for impl in os.environ.get("PYR_IMPLS", "stream,mma").split(","):
+    for impl in os.environ.get("PYR_IMPLS", "umma,stream").split(","):
         os.environ["VHR_PYRDOWN_IMPL"] = impl
         for L in (2, 4):
             out = eng.pyrdown(fr, L)

@@ -15,7 +15,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["api.cu", "synth.cu", "pyrdown.cu", "pyrdown_stream.cu", "pyrdown_mma.cu", "pyrdown_umma.cu", "bandpass.cu", "collapse_sep.cu", "roi.cu", "bpm.cu", "ica.cu", "degrade.cu", "hostpath.cu"]
+SOURCES = ["api.cu", "synth.cu", "pyrdown.cu", "pyrdown_stream.cu", "pyrdown_umma.cu", "bandpass.cu", "collapse_sep.cu", "roi.cu", "bpm.cu", "ica.cu", "degrade.cu", "hostpath.cu"]
 LIB = os.path.join(HERE, "libvhr_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]

@@ -23,11 +23,9 @@
 #include "common.cuh"
 #include <stdlib.h>
 
-// streaming kernels for 16-aligned widths (pyrdown_stream.cu, pyrdown_mma.cu); VHR_ERR_UNSUPPORTED when the shape is not eligible
+// tensor-core kernel (pyrdown_umma.cu) and streaming kernel (pyrdown_stream.cu); VHR_ERR_UNSUPPORTED when the shape is not eligible
 int vhr_pyrdown_umma(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int W, int levels, float* d_level,
                      cudaStream_t stream);
-int vhr_pyrdown_mma(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int W, int levels, float* d_level,
-                    cudaStream_t stream);
 int vhr_pyrdown_stream(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int W, int levels, float* d_level,
                        cudaStream_t stream);
 
@@ -346,21 +344,15 @@ extern "C" int vhr_pyrdown_cascade(vhr_ctx* ctx, const uint8_t* d_frames, int T,
     VHR_REQUIRE(ctx, levels >= 1 && levels <= VHR_MAX_LEVELS, "levels must be 1..6");
     VHR_REQUIRE(ctx, W <= 8192, "W > 8192 unsupported");
     {
-        // Dispatch: the tcgen05 kernel (pyrdown_umma.cu: 4 levels, W % 80 == 0), then
-        // the streaming kernel (pyrdown_stream.cu: W % 16 == 0, W % 64 == 0 for >= 3 levels), then the
-        // private-pipeline tensor-core kernel (pyrdown_mma.cu: W % 16 == 0 and W % 2^levels == 0, <= 5 levels; slower, but
-        // it takes the 16-aligned widths the streaming kernel does not), then the generic kernel below.  Test /
-        // measurement hooks: VHR_PYRDOWN_IMPL=stream skips the tcgen05 kernel, =mma tries the private-pipeline kernel first, VHR_PYRDOWN_GENERIC=1 forces
-        // the generic kernel.
+        // Dispatch: the tcgen05 kernel (pyrdown_umma.cu: 4 levels, W % 80 == 0), then the streaming kernel
+        // (pyrdown_stream.cu: W % 16 == 0, W % 64 == 0 for >= 3 levels), then the generic kernel below.  Test /
+        // measurement hooks: VHR_PYRDOWN_IMPL=stream skips the tcgen05 kernel, VHR_PYRDOWN_GENERIC=1 forces the generic one.
         const char* force = getenv("VHR_PYRDOWN_GENERIC");
         const char* impl = getenv("VHR_PYRDOWN_IMPL");
         if (!(force && force[0] == '1')) {
             int rc = VHR_ERR_UNSUPPORTED;
-            const char im = impl ? impl[0] : 'u';
-            if (im == 'u') rc = vhr_pyrdown_umma(ctx, d_frames, T, H, W, levels, d_level, (cudaStream_t)stream);
-            if (im == 'm') rc = vhr_pyrdown_mma(ctx, d_frames, T, H, W, levels, d_level, (cudaStream_t)stream);
+            if (!(impl && impl[0] == 's')) rc = vhr_pyrdown_umma(ctx, d_frames, T, H, W, levels, d_level, (cudaStream_t)stream);
             if (rc == VHR_ERR_UNSUPPORTED) rc = vhr_pyrdown_stream(ctx, d_frames, T, H, W, levels, d_level, (cudaStream_t)stream);
-            if (rc == VHR_ERR_UNSUPPORTED && im != 'm') rc = vhr_pyrdown_mma(ctx, d_frames, T, H, W, levels, d_level, (cudaStream_t)stream);
             if (rc != VHR_ERR_UNSUPPORTED) return rc;
         }
     }

@@ -1,6 +1,6 @@
 // Streaming CUDA-core form of the fused pyrDown cascade (W % 16 == 0; W % 64 == 0 for >= 3 levels; 16-byte aligned
 // frames).  Since round 2 it serves the shapes and level counts the tensor-core kernel (pyrdown_umma.cu: 4 levels,
-// W % 80 == 0) does not take; pyrdown_mma.cu and the generic kernel in pyrdown.cu cover the rest, same arithmetic.
+// W % 80 == 0) does not take; the generic kernel in pyrdown.cu covers the rest, same arithmetic.
 //
 // Same spec as pyrdown.cu (cv2.pyrDown float32 semantics; levels 1-2 exact integers * 2^-8l).  Current form (v6;
 // the stage-by-stage history with the ncu captures is in profiles/README.md, the design in DESIGN.md section 4.1b):

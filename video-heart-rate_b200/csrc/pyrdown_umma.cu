@@ -1,6 +1,6 @@
 // Fused 4-level pyrDown cascade on the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in TMEM).
 // uint8 (T,H,W,3) -> float32 (T,h4,w4,3); W % 80 == 0, 16-byte aligned frames, levels == 4.  Every other shape takes
-// pyrdown_stream.cu / pyrdown_mma.cu / pyrdown.cu.  Same spec as pyrdown.cu (cv2.pyrDown float32 semantics; no
+// pyrdown_stream.cu / pyrdown.cu.  Same spec as pyrdown.cu (cv2.pyrDown float32 semantics; no
 // reference code exists for this stage; oracle/evm.py:pyrdown_cascade).
 //
 // Why: the streaming kernel (pyrdown_stream.cu) is instruction-issue bound at 49 % of the HBM roofline (~220
