@@ -31,7 +31,11 @@
 // owner, 2-5 level-2 warps (TMEM lane quarter = warp % 4), 6-7 level-3 warps, 8 level-4 warp.  Bounded buffers with
 // full / empty mbarriers between every pair of stages; TMEM holds two 240-column accumulators.
 // Exactness: level 2 is an exact integer (< 2^24); levels 3-4 accumulate in float32 (tests: <= 1e-4 of full scale,
-// measured ~1e-7).
+// measured ~2e-7).
+// Two things the ncu captures taught (profiles/README.md, round 2): (1) the single-thread role loops must be cheap -- they
+// run warp-uniform so that descriptors and barrier addresses stay in uniform registers and one elected lane issues; with
+// ~50 instructions per k-step on one thread the whole kernel waited for its issuers.  (2) The epilogue must be small code:
+// five unrolled chunk copies per strip (19 KB) starved the level-2 warps on instruction fetch; one instance, five trips.
 #include "common.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
