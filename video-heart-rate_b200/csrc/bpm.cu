@@ -476,8 +476,7 @@ extern "C" int vhr_bpm_fft(vhr_ctx* ctx, const double* d_trace, int n_trace, int
     // few windows: spread each over a cluster; many windows already fill the GPU (and the split repeats the detrend)
     int nsplit = 1;
     while (nsplit < MAXSPLIT && (long long)n_win * nsplit * 2 <= 2LL * ctx->num_sms) nsplit *= 2;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)n_win * nsplit, 1, 1);
     cfg.blockDim = dim3(BT, 1, 1);
     cfg.dynamicSmemBytes = smem;

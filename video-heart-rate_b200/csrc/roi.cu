@@ -197,8 +197,6 @@ __global__ void __launch_bounds__(RT) poly_mean_kernel(const Tpix* __restrict__ 
         bx0 = min(bx0, verts[i].x); bx1 = max(bx1, verts[i].x);
         by0 = min(by0, verts[i].y); by1 = max(by1, verts[i].y);
     }
-    // every |coordinate| and every row <= 16383: the 32-bit form of the edge arithmetic is exact
-    const bool small = n > 0 && bx0 >= -16383 && by0 >= -16383 && bx1 <= 16383 && by1 <= 16383 && H <= 16383;
     bx0 = max(bx0, 0); by0 = max(by0, 0); bx1 = min(bx1, W - 1); by1 = min(by1, H - 1);
     const int bw = bx1 - bx0 + 1, bh = by1 - by0 + 1;
     const Tpix* fr = frames + (size_t)t * H * W * 3;
