@@ -192,6 +192,34 @@ def test_pyrdown_tensor_core_accumulators_are_exact(vhr, eng, case):
         np.testing.assert_array_equal(acc.cpu().numpy()[:tile["nr"]], D[:tile["nr"]])
 
 
+def test_pyrdown_tensor_core_kernel_many_shapes_two_streams(vhr, eng, monkeypatch):
+    """The weight blobs of the tensor-core kernel are cached per context and frame shape (8 slots) and are read by kernels
+    on whatever stream the call was made on: twelve shapes interleaved on two streams, twice over (the second round evicts
+    and reloads blobs), give the bits of a plain single-stream run."""
+    import torch
+    rng = np.random.default_rng(5)
+    shapes = [(64 + 16 * k, 160 + 80 * (k % 4)) for k in range(12)]
+    clips = [torch.as_tensor(rng.integers(0, 256, (3, h, w, 3), dtype=np.uint8), device=eng.tdev) for h, w in shapes]
+    monkeypatch.setenv("VHR_PYRDOWN_IMPL", "stream")
+    refs = [eng.pyrdown(c, 4).clone() for c in clips]
+    monkeypatch.delenv("VHR_PYRDOWN_IMPL")
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for rnd in range(2):
+        outs = []
+        for k, c in enumerate(clips):
+            with torch.cuda.stream(s1 if (k + rnd) % 2 == 0 else s2):
+                outs.append(eng.pyrdown(c, 4))
+        torch.cuda.synchronize()
+        for got, ref in zip(outs, refs):
+            assert rel_err(got.cpu().numpy(), ref.cpu().numpy()) <= 2e-6
+        if rnd == 0:
+            first = [o.clone() for o in outs]
+        else:
+            for a, b in zip(outs, first):
+                assert torch.equal(a, b)
+
+
 def test_pyrdown_tensor_core_kernel_constant_and_extremes(vhr, eng):
     """All-255 frames exercise the largest accumulators (255 * 256 per column, 255 * 65536 per level-2 value): every level
     of a constant image is that constant, exactly; a single bright pixel checks every weight of the composite filters."""
