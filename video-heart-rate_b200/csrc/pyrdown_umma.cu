@@ -15,8 +15,9 @@
 //     transposition anywhere), A is the banded weight slice.  The band is shift-invariant (32 input rows = 8 output
 //     rows), so ONE 8 KB zero-padded band in shared memory serves every k-step through the descriptor's start address;
 //     the few slices that touch a frame border (reflect-101 folded into the weights by the host, cv2 semantics at both
-//     levels) are kept as explicit 4 KB slices.  The 22x zero padding of the band costs nothing: the tensor pipe is 40 %
-//     busy at the HBM-bound rate.
+//     levels) are kept as explicit 4 KB slices.  A k-step only has weights for ~11 consecutive level-2 rows, so it is issued
+//     as an M = 64 MMA on the half of the tile that holds them (both halves at the seam); the remaining 11x zero
+//     padding costs nothing: the tensor pipe is far from busy at the HBM-bound rate.
 //   * HORIZONTAL in registers, on data that is already 4x smaller.  An epilogue thread owns one level-2 row: it reads its
 //     240 accumulators (tcgen05.ld) and applies the same 13-tap filter with compile-time weights; 30 accumulator columns
 //     and three level-2 pixels are carried from strip to strip, so strips do not overlap (each strip emits the 20 level-2
@@ -90,7 +91,9 @@ struct UmmaArgs {
     const uint8_t* blob;                  // band + special slices (global), blob_bytes
     int blob_bytes;
     UmmaTile tile[MAX_TILES];
-    alignas(4) unsigned short code[MAX_TILES][MAX_KS];   // byte offset >> 4 of the A slice inside the blob (read in pairs: one stage)
+    alignas(4) unsigned short code[MAX_TILES][MAX_KS];   // per k-step (read in pairs = one stage): bits 0-11 byte offset >> 4 of the
+                                                         // 128-row A slice inside the blob, bits 12-13 which 64-row halves carry
+                                                         // weights, bits 14-15 which of them this k-step writes first in a strip
     int wsp[3][13];                       // horizontal weights of level-2 pixels 0, 1 and w2 - 1 (window coordinates)
     uint32_t* dbg;                        // optional: raw accumulators of (dbg_item, dbg_strip), 128 x 240
     int dbg_item, dbg_strip;
@@ -172,7 +175,10 @@ constexpr uint64_t A_DESC_HI = (uint64_t)((256u >> 4) | (1u << 14)) << 32 | (uin
 constexpr uint64_t B_DESC_HI = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32 | (uint64_t)(8192u >> 4) << 16;
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D = s32 (2 at [4,6)), A = B = unsigned 8 bit (0 at [7,10) and
 // [10,13)), A K-major (0 at 15), B MN-major (1 at 16), N >> 3 at [17,23), M >> 4 at [24,29).
-constexpr uint32_t IDESC = (2u << 4) | (1u << 16) | ((uint32_t)(NB >> 3) << 17) | ((128u >> 4) << 24);
+// M = 64: a k-step (32 input rows) only has weights for ~11 consecutive level-2 rows, i.e. for one 64-row half of the
+// tile (two at the seam), so only that half is multiplied: half the tensor work (and power) of the M = 128 form.  An
+// M = 64 accumulator occupies 16 lanes of each TMEM lane quarter: row i of half h sits in lane 32 (i / 16) + 16 h + i % 16.
+constexpr uint32_t IDESC = (2u << 4) | (1u << 16) | ((uint32_t)(NB >> 3) << 17) | ((64u >> 4) << 24);
 
 __device__ __forceinline__ int refl101(int i, int n) {
     if (i < 0) i = -i;
@@ -320,8 +326,18 @@ __global__ void __launch_bounds__(THREADS, 1) pyrdown_umma_kernel(const __grid_c
                     tc_fence_after();
                     if (elect_one() && !(a.mode & 2)) {
                         const uint32_t b0 = b_base + st * (STAGE_BYTES >> 4);
-                        tc_mma_i8(d_tmem, A_DESC_HI | (uint64_t)((a_base + (cc & 0xFFFFu)) & 0x3FFFu), B_DESC_HI | (uint64_t)(b0 & 0x3FFFu), IDESC, kp > 0);
-                        tc_mma_i8(d_tmem, A_DESC_HI | (uint64_t)((a_base + (cc >> 16)) & 0x3FFFu), B_DESC_HI | (uint64_t)((b0 + 256u) & 0x3FFFu), IDESC, 1u);
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {                    // the stage's two k-steps
+                            const uint32_t c = j ? cc >> 16 : cc & 0xFFFFu;
+                            const uint64_t bdesc = B_DESC_HI | (uint64_t)((b0 + 256u * j) & 0x3FFFu);
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {                // the tile's two 64-row halves
+                                if ((c >> (12 + h)) & 1u)
+                                    tc_mma_i8(d_tmem + ((uint32_t)(16 * h) << 16),
+                                              A_DESC_HI | (uint64_t)((a_base + (c & 0xFFFu) + 128u * h) & 0x3FFFu), bdesc, IDESC,
+                                              ((c >> (14 + h)) & 1u) ^ 1u);
+                            }
+                        }
                     }
                     if (elect_one()) tc_commit(bar_empty(st));
                     __syncwarp();
@@ -334,14 +350,14 @@ __global__ void __launch_bounds__(THREADS, 1) pyrdown_umma_kernel(const __grid_c
     } else if (warp < 6) {
         // ---- level-2 warps: accumulators -> level 2 (13-tap) -> horizontal pass of level 3 ------------------------------
         const int q = warp & 3;
-        const int m = 32 * q + lane;
+        const int m = 64 * (lane >> 4) + 16 * q + (lane & 15);           // TMEM lane 32 q + lane holds this level-2 row (M = 64 halves)
         const uint32_t tlane = tmem_base + ((uint32_t)(32 * q) << 16);
         const uint32_t ridx = 4u * ((m & 1) * L3H_ODD + (m >> 1));
         uint32_t sc = 0;
         for (long long item = blockIdx.x; item < a.items; item += gridDim.x) {
             const int f = (int)(item / a.ntiles);
             const int t = (int)(item - (long long)f * a.ntiles);
-            const bool active = 32 * q < a.tile[t].nr;
+            const bool active = 16 * q < a.tile[t].nr;
             uint32_t v[78];                      // [0, 30): columns carried from the previous chunk, [30, 78): this chunk
             float p3[3][3];                      // the three level-2 pixels before this chunk
 #pragma unroll
@@ -526,6 +542,7 @@ struct UmmaPlan {
     int ntiles = 0, nstrips = 0, nspecial = 0;
     UmmaTile tile[MAX_TILES];
     unsigned short code[MAX_TILES][MAX_KS];
+    unsigned char half[MAX_TILES][MAX_KS];      // bit h: the k-step has weights for rows 64 h .. 64 h + 63
     int wsp[3][13];
     std::vector<uint8_t> blob;
 };
@@ -589,6 +606,12 @@ int make_plan_n4(int H, int W, int n4, UmmaPlan& p) {
                     if (wv != gv) generic = false;
                     sl[canon(m, k)] = (uint8_t)wv;
                 }
+            // which 64-row halves of the tile this k-step has weights for (rows past the tile do not count)
+            unsigned halves = 0;
+            for (int m = 0; m < tl.nr; ++m)
+                for (int k = 0; k < 32; ++k)
+                    if (sl[canon(m, k)]) halves |= 1u << (m >> 6);
+            p.half[t][ks] = (unsigned char)halves;
             if (generic && ks <= 16) {
                 p.code[t][ks] = (unsigned short)(((16 - ks) * 256) >> 4);
             } else {
@@ -729,7 +752,13 @@ static int umma_launch(vhr_ctx* ctx, const uint8_t* d_frames, int T, int H, int 
     a.blob_bytes = (int)plan.blob.size();
     for (int t = 0; t < plan.ntiles; ++t) {
         a.tile[t] = plan.tile[t];
-        for (int ks = 0; ks < MAX_KS; ++ks) a.code[t][ks] = plan.code[t][ks];
+        unsigned seen = 0;
+        for (int ks = 0; ks < MAX_KS; ++ks) {
+            const unsigned halves = ks < plan.tile[t].nks ? plan.half[t][ks] : 0u;
+            const unsigned first = halves & ~seen;          // the MMA that must overwrite the half instead of accumulating
+            seen |= halves;
+            a.code[t][ks] = (unsigned short)((plan.code[t][ks] & 0xFFFu) | (halves << 12) | (first << 14));
+        }
     }
     memcpy(a.wsp, plan.wsp, sizeof(a.wsp));
     a.dbg = d_acc; a.dbg_item = acc_item; a.dbg_strip = acc_strip;
