@@ -9,7 +9,7 @@ eng = vhr.Engine(0)
 T = int(os.environ.get("PYR_T", 1800)); W = int(os.environ.get("PYR_W", 1920)); H = int(os.environ.get("PYR_H", 1080))
 fr = eng.synth_clip(vhr.SynthSpec(T=T, H=H, W=W, fps=30.0, pulse_hz=1.2, seed=0, clip=0))
 res = {}
-for mode in os.environ.get("VHR_UMMA_MODES", "0").split(","):
+for rep, mode in enumerate(os.environ.get("VHR_UMMA_MODES", "0").split(",")):
     os.environ["VHR_UMMA_MODE"] = mode
     o = eng.pyrdown(fr, 4)
     torch.cuda.synchronize()
@@ -18,5 +18,5 @@ for mode in os.environ.get("VHR_UMMA_MODES", "0").split(","):
     for _ in range(5):
         eng.pyrdown(fr, 4, out=o)
     e1.record(); torch.cuda.synchronize()
-    res["mode" + mode] = round(e0.elapsed_time(e1) / 5, 4)
+    res[f"mode{mode}_{rep}"] = round(e0.elapsed_time(e1) / 5, 4)
 print(json.dumps(res))

@@ -46,16 +46,19 @@
 namespace {
 
 #ifndef UMMA_NSTAGE
-#define UMMA_NSTAGE 6
+#define UMMA_NSTAGE 9
 #endif
-constexpr int NSTAGE = UMMA_NSTAGE;     // image stages of 64 rows x 256 bytes = two k-steps
+constexpr int NSTAGE = UMMA_NSTAGE;     // image stages of 64 rows x 256 bytes = two k-steps (6 / 8 / 9 stages: 1.892 / 1.860 / 1.854 ms)
 constexpr int STAGE_BYTES = 16384;
 constexpr int PX = 20;                  // level-2 pixels per strip
 constexpr int NB = 12 * PX;             // fresh bytes per strip = MMA N
 constexpr int MAX_N4 = 29;              // level-4 rows per tile (4 n + 9 level-2 rows <= 128)
 constexpr int MAX_TILES = 12;
 constexpr int MAX_KS = 18;              // k-steps per tile, even (band offsets 0..16; a 17th / 18th step only ever meets unused rows)
-constexpr int MAX_SPECIAL = 8;
+#ifndef UMMA_MAX_SPECIAL
+#define UMMA_MAX_SPECIAL 6
+#endif
+constexpr int MAX_SPECIAL = UMMA_MAX_SPECIAL;
 constexpr int BAND_BYTES = 8192;
 constexpr int SLICE_BYTES = 4096;
 constexpr int L3H_PITCH = 144;          // floats per column: even rows at 0.., odd rows at 80.. (conflict-free both ways)
