@@ -317,10 +317,11 @@ def _guards_intact(raw, n, fill):
 
 
 @pytest.mark.parametrize("case", [(5, 61, 67, 3), (3, 97, 131, 4), (2, 40, 3840, 4), (9, 135, 248, 4), (260, 36, 64, 2),
-                                  (2, 1080, 1920, 4), (4, 33, 700, 3)])
+                                  (2, 1080, 1920, 4), (4, 33, 700, 3), (40, 90, 720, 4), (7, 135, 240, 4)])
 def test_guard_bands_survive_every_kernel(vhr, eng, case):
     """Every output buffer of the EVM + ROI + BPM path sits between 4 KiB guard bands of a known pattern;
-    odd sizes, W = 3840 (512-thread pyrDown), shares crossing frames, TMA and scalar paths.  Hand-rolled
+    odd sizes, W = 3840 (512-thread pyrDown), shares crossing frames, TMA and scalar paths, the tensor-core pyrDown
+    (W % 80 == 0, 4 levels: one tile and several, more items than CTAs).  Hand-rolled
     bulk copies with computed byte counts must not write one byte outside their tensor."""
     import torch
     T, H, W, L = case
