@@ -233,8 +233,9 @@ def run_gpu(args):
     dims = eng.pyr_dims(W, H, LEVELS)
     wl, hl = dims[-1]
     p = wl * hl
-    bytes_per_frame = 18 * W * H + 48 * p                      # BASELINE.md section 3, fp32 output
-    collapse_bytes_per_frame = 15 * W * H + 12 * p             # S3: read L4 + u8 frame, write fp32 frame
+    u8out = args.out == "u8"                                   # saturated uint8 magnified frames instead of float32 ones
+    bytes_per_frame = (9 if u8out else 18) * W * H + 48 * p    # BASELINE.md section 3 (fp32 output: the contract figure)
+    collapse_bytes_per_frame = (6 if u8out else 15) * W * H + 12 * p   # S3: read L4 + u8 frame, write the output frame
     peak_gbs, peak_src = peaks()
 
     # ---- resident inputs -------------------------------------------------------------------
@@ -248,7 +249,7 @@ def run_gpu(args):
     poly = args.roi == "poly"
     polys_np, nverts_np = host.face_polygons(np.broadcast_to(lm, (T,) + lm.shape), W, H, n_vertices=36)
     polys_d, nverts_d = torch.as_tensor(polys_np, device=dev), torch.as_tensor(nverts_np, device=dev)
-    out = torch.empty((T, H, W, 3), dtype=torch.float32, device=dev)
+    out = torch.empty((T, H, W, 3), dtype=torch.uint8 if u8out else torch.float32, device=dev)
     lvl = torch.empty((T, hl, wl, 3), dtype=torch.float32, device=dev)
     starts = torch.zeros(1, dtype=torch.int32, device=dev)      # BPM window list lives on the device
     lens = torch.full((1,), T, dtype=torch.int32, device=dev)
@@ -267,9 +268,11 @@ def run_gpu(args):
         eng.bandpass(lvl, fps, F_LO, F_HI, ALPHA, out=lvl)
         if timed: e[2].record(stream)
         if poly:
-            _, _, means = eng.collapse(lvl, fr, LEVELS, out_f32=out, out_u8=False, polys=polys_d, nverts=nverts_d)
+            _, _, means = eng.collapse(lvl, fr, LEVELS, out_f32=False if u8out else out, out_u8=out if u8out else False,
+                                       polys=polys_d, nverts=nverts_d)
         else:
-            _, _, means = eng.collapse(lvl, fr, LEVELS, out_f32=out, out_u8=False, rects=rects)
+            _, _, means = eng.collapse(lvl, fr, LEVELS, out_f32=False if u8out else out, out_u8=out if u8out else False,
+                                       rects=rects)
         if timed: e[3].record(stream)
         # green column(s) of the (T,K,3) trace, read in place (row / column strides)
         bpm, kbin = eng.bpm_fft(means[:, :, 1] if poly else means[:, 0, 1], starts, lens, fps, ANALYSIS_BAND,
@@ -409,7 +412,8 @@ def run_gpu(args):
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
                 "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": desc, "levels": LEVELS, "band_hz": [F_LO, F_HI], "alpha": ALPHA,
+                "config": {"workload": desc.replace("fp32 out", "uint8 out (--out u8; not the contract configuration)") if u8out else desc,
+                           "levels": LEVELS, "band_hz": [F_LO, F_HI], "alpha": ALPHA,
                            "frames_per_step_per_gpu": T, "resident_clips_per_gpu": n_res,
                            "roi": "forehead + 2 cheeks, 36-vertex polygons (fused row masks)" if poly else "1 cheek rectangle",
                            "bpm": "whole-clip window, float32 detrend + FFT peak",
@@ -417,7 +421,7 @@ def run_gpu(args):
                            "host_affinity": affinity},
                 "roofline": {"bound": "hbm", "kernel": "collapse_sep_kernel", "achieved": achieved, "peak": peak_gbs,
                              "unit": "GB/s", "frac": achieved / peak_gbs,
-                             "traffic": recorded_traffic("collapse_sep_kernel")[0] if args.workload == "c4" else None,
+                             "traffic": recorded_traffic("collapse_sep_kernel")[0] if args.workload == "c4" and not u8out else None,
                              "traffic_source": f"ncu --set full capture of the same command, {recorded_traffic('collapse_sep_kernel')[1]}",
                              "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": collapse_bytes_per_frame * T, "ms_per_launch": col_ms},
@@ -448,6 +452,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--affinity", default="off", choices=["off", "on", "auto"],
                     help="pin each rank to its share of the host cores (auto: when N > 1)")
+    ap.add_argument("--out", default="f32", choices=["f32", "u8"], help="magnified frames: float32 (the BASELINE contract) or saturated uint8")
     ap.add_argument("--roi", default="rect", choices=["rect", "poly"], help="ROI stage: cheek rectangle, or forehead + cheek polygons")
     args = ap.parse_args()
     if args.impl == "reference":
