@@ -300,6 +300,34 @@ def test_bpm_fft_strided_views(vhr, eng):
         assert float(a[w]) == exp and col == 2
 
 
+@pytest.mark.parametrize("case", [(1, 8000), (1, 8400), (3, 4000), (37, 900), (200, 64), (1, 9)])
+def test_bpm_fft_cluster_split_matches_the_oracle(vhr, eng, case):
+    """vhr_bpm_fft spreads a window over a thread-block cluster when windows are few (8 CTAs for one window, 4 / 2 / 1 as
+    the count grows): windows at the shared-memory limit (8 000 samples = 224 KB per CTA), past it (error, not a crash),
+    short ones whose shares of the band are empty in most CTAs, and many windows (no split) all give the oracle's BPM."""
+    import torch
+    from video_heart_rate_b200.pipeline import ANALYSIS_BAND
+    nw, n = case
+    rng = np.random.default_rng(nw * 7 + n)
+    fs = 30.0
+    t = np.arange(n + nw) / fs
+    tr = 0.3 * rng.standard_normal(n + nw) + np.sin(2 * np.pi * (0.9 + 0.03 * (n % 17)) * t) + 100.0
+    d = torch.as_tensor(tr, device=eng.tdev)
+    starts, lens = list(range(nw)), [n] * nw
+    if n * 28 > 227 * 1024:
+        with pytest.raises(Exception):
+            eng.bpm_fft(d, starts, lens, fs, ANALYSIS_BAND, detrend=vhr.DETREND_F32)
+        return
+    bpm, kbin = eng.bpm_fft(d, starts, lens, fs, ANALYSIS_BAND, detrend=vhr.DETREND_F32)
+    for w in range(nw):
+        g = tr[w:w + n].astype(np.float32)
+        exp = obpm.estimate_bpm_analysis(g - np.mean(g), fs)
+        if exp is None or exp[0] is None:
+            assert np.isnan(float(bpm[w])) and int(kbin[w]) == -1
+        else:
+            assert float(bpm[w]) == exp[0] and int(kbin[w]) == exp[1], (w, float(bpm[w]), exp[:2])
+
+
 # ------------------------------------------------------------------ safety
 GUARD = 4096
 
