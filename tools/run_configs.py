@@ -187,9 +187,13 @@ def run_c5(eng, vhr, n=512, seconds=10.0):
     bpm = got[:, 0]
     truth = np.array([60.0 * f for (_, _, _, f, _) in wins])
     err = np.abs(bpm - truth)
-    by_noise = {str(sg): float(np.nanmean(err[[j for j, w in enumerate(wins) if w[2] == sg]])) for sg in NOISE}
-    by_res = {str(h): float(np.nanmean(err[[j for j, w in enumerate(wins) if w[0] == h]])) for h in RES}
-    by_fps = {str(fp): float(np.nanmean(err[[j for j, w in enumerate(wins) if w[1] == fp]])) for fp in FPS}
+    def group_mae(pos, key):               # mean |error| of the windows whose field `pos` is `key` (None: no such window)
+        sel = err[[j for j, w in enumerate(wins) if w[pos] == key]]
+        sel = sel[~np.isnan(sel)]
+        return float(sel.mean()) if sel.size else None
+    by_noise = {str(sg): group_mae(2, sg) for sg in NOISE}
+    by_res = {str(h): group_mae(0, h) for h in RES}
+    by_fps = {str(fp): group_mae(1, fp) for fp in FPS}
     frames = sum(int(w[1] * seconds) for w in wins)
     ok = None
     try:
